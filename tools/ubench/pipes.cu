@@ -1,0 +1,146 @@
+// Issue-slot / pipe throughput microbenchmark for the ACS instruction recipes.
+// Measures warp-instructions per clock per SM for single ops and for ACS-shaped
+// mixes, so DESIGN.md's ALU roofline denominator is a measured number.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipes pipes.cu && ./pipes
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+  fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
+
+constexpr int NCH = 8;       // independent chains per thread
+constexpr int ITERS = 4096;
+
+// op codes
+enum { OP_FADD, OP_FADD2, OP_FMNMX, OP_IADD, OP_IMAD, OP_SHF, OP_LOP, OP_SETPSEL,
+       MIX_FADD_FMNMX, MIX_FADD_IADD, MIX_FADD_IMAD, MIX_FMNMX_IADD,
+       MIX_ACS_A,   // 2 FADD + FMNMX + IADD + SHF           (5 slots / state-update)
+       MIX_ACS_B,   // 2 FADD + FSETP + SELP + @p OR         (5 slots)
+       MIX_ACS_C,   // FADD2 (2 updates) + 2x(FMNMX + IADD + SHF)   (3.5 slots / update)
+       MIX_ACS_D,   // FADD2 + 2x(FMNMX + FADD(diff) + SHF)
+       MIX_ACS_E,   // FADD2 + 2x(FMNMX + IMAD(diff) + SHF)
+       MIX_ACS_F,   // 2 FADD + FMNMX + FADD(diff) + SHF
+       NOPS };
+static const char* names[NOPS] = {"FADD", "FADD2", "FMNMX", "IADD3", "IMAD", "SHF", "LOP3", "FSETP+SELP",
+  "FADD+FMNMX", "FADD+IADD3", "FADD+IMAD", "FMNMX+IADD3",
+  "ACS_A 2FADD+FMNMX+IADD+SHF", "ACS_B 2FADD+FSETP+SELP+@pOR", "ACS_C FADD2+2(FMNMX+IADD+SHF)",
+  "ACS_D FADD2+2(FMNMX+FADDdiff+SHF)", "ACS_E FADD2+2(FMNMX+IMADdiff+SHF)", "ACS_F 2FADD+FMNMX+FADDdiff+SHF"};
+// instructions per chain-iteration for each op
+static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5};
+
+template <int OP>
+__global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, long long* cyc) {
+  float f[NCH], g[NCH];
+  uint32_t u[NCH], v[NCH];
+  unsigned long long d[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    f[i] = threadIdx.x * 0.5f + i; g[i] = f[i] + 1.f; u[i] = threadIdx.x + i; v[i] = u[i] * 3;
+    d[i] = ((unsigned long long)__float_as_uint(f[i]) << 32) | __float_as_uint(g[i]);
+  }
+  unsigned long long c2 = ((unsigned long long)__float_as_uint(cf) << 32) | __float_as_uint(cf);
+  long long t0 = clock64();
+  for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      if (OP == OP_FADD) { asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i])); asm volatile("add.f32 %0, %0, %1;" : "+f"(g[i]) : "f"(f[i])); }
+      if (OP == OP_FADD2) { asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(c2)); asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(c2) : "l"(d[i])); }
+      if (OP == OP_FMNMX) { asm volatile("min.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i])); asm volatile("max.f32 %0, %0, %1;" : "+f"(g[i]) : "f"(f[i])); }
+      if (OP == OP_IADD) { asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(v[i])); asm volatile("add.s32 %0, %0, %1;" : "+r"(v[i]) : "r"(u[i])); }
+      if (OP == OP_IMAD) { asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(u[i]) : "r"(v[i])); asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(v[i]) : "r"(u[i])); }
+      if (OP == OP_SHF) { asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(u[i]) : "r"(v[i])); asm volatile("shf.l.wrap.b32 %0, %1, %0, 3;" : "+r"(v[i]) : "r"(u[i])); }
+      if (OP == OP_LOP) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[i]) : "r"(v[i]), "r"(cu)); asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(v[i]) : "r"(u[i]), "r"(cu)); }
+      if (OP == OP_SETPSEL) asm volatile("{.reg .pred p; setp.lt.f32 p, %0, %1; selp.f32 %0, %0, %1, p;}" : "+f"(f[i]) : "f"(g[i]));
+      if (OP == MIX_FADD_FMNMX) { asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i])); asm volatile("min.f32 %0, %0, %1;" : "+f"(g[i]) : "f"(f[i])); }
+      if (OP == MIX_FADD_IADD) { asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i])); asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(__float_as_uint(f[i]))); }
+      if (OP == MIX_FADD_IMAD) { asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i])); asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(u[i]) : "r"(__float_as_uint(f[i]))); }
+      if (OP == MIX_FMNMX_IADD) { asm volatile("min.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(__uint_as_float(u[i]))); asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(__float_as_uint(f[i]))); }
+      if (OP == MIX_ACS_A) {
+        float c0, c1; int df;
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(c0) : "f"(f[i]), "f"(cf));
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(c1) : "f"(g[i]), "f"(cf));
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(f[i]) : "f"(c0), "f"(c1));
+        asm volatile("sub.s32 %0, %1, %2;" : "=r"(df) : "r"(__float_as_int(c1)), "r"(__float_as_int(c0)));
+        asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(u[i]) : "r"(df));
+      }
+      if (OP == MIX_ACS_B) {
+        float c0, c1;
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(c0) : "f"(f[i]), "f"(cf));
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(c1) : "f"(g[i]), "f"(cf));
+        asm volatile("{.reg .pred p; setp.lt.f32 p, %3, %2; selp.f32 %0, %3, %2, p; @p or.b32 %1, %1, %4;}"
+                     : "=f"(f[i]), "+r"(u[i]) : "f"(c0), "f"(c1), "r"(1u << i));
+      }
+      if (OP == MIX_ACS_C || OP == MIX_ACS_D || OP == MIX_ACS_E) {
+        unsigned long long cc;
+        asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(cc) : "l"(d[i]), "l"(c2));
+        float c0 = __uint_as_float((uint32_t)cc), c1 = __uint_as_float((uint32_t)(cc >> 32));
+        float n0, n1; int d0, d1;
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(n0) : "f"(c0), "f"(c1));
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(n1) : "f"(c1), "f"(cf));
+        if (OP == MIX_ACS_C) {
+          asm volatile("sub.s32 %0, %1, %2;" : "=r"(d0) : "r"(__float_as_int(c1)), "r"(__float_as_int(c0)));
+          asm volatile("sub.s32 %0, %1, %2;" : "=r"(d1) : "r"(__float_as_int(c0)), "r"(__float_as_int(c1)));
+        } else if (OP == MIX_ACS_D) {
+          float e0, e1;
+          asm volatile("sub.f32 %0, %1, %2;" : "=f"(e0) : "f"(c1), "f"(c0));
+          asm volatile("sub.f32 %0, %1, %2;" : "=f"(e1) : "f"(c0), "f"(c1));
+          d0 = __float_as_int(e0); d1 = __float_as_int(e1);
+        } else {
+          asm volatile("mad.lo.s32 %0, %1, -1, %2;" : "=r"(d0) : "r"(__float_as_int(c0)), "r"(__float_as_int(c1)));
+          asm volatile("mad.lo.s32 %0, %1, -1, %2;" : "=r"(d1) : "r"(__float_as_int(c1)), "r"(__float_as_int(c0)));
+        }
+        asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(u[i]) : "r"(d0));
+        asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(v[i]) : "r"(d1));
+        d[i] = ((unsigned long long)__float_as_uint(n1) << 32) | __float_as_uint(n0);
+      }
+      if (OP == MIX_ACS_F) {
+        float c0, c1, e0;
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(c0) : "f"(f[i]), "f"(cf));
+        asm volatile("add.f32 %0, %1, %2;" : "=f"(c1) : "f"(g[i]), "f"(cf));
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(f[i]) : "f"(c0), "f"(c1));
+        asm volatile("sub.f32 %0, %1, %2;" : "=f"(e0) : "f"(c1), "f"(c0));
+        asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(u[i]) : "r"(__float_as_int(e0)));
+      }
+    }
+  }
+  long long t1 = clock64();
+  float acc = 0;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) acc += f[i] + g[i] + (float)u[i] + (float)v[i] + (float)(d[i] & 0xffff);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+int run(int sms, int threads, float* out, long long* cyc) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  k<OP><<<sms, threads>>>(out, 0.25f, 7u, cyc);   // warm
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(e0));
+  k<OP><<<sms, threads>>>(out, 0.25f, 7u, cyc);
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  long long h[1024]; CK(cudaMemcpy(h, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
+  double mean = 0; for (int i = 0; i < sms; ++i) mean += h[i]; mean /= sms;
+  double winstr = (double)(threads / 32) * ITERS * NCH * ipc_n[OP];   // per SM
+  printf("{\"op\": \"%s\", \"threads_per_sm\": %d, \"warp_inst_per_clk_per_sm\": %.3f, \"ms\": %.3f, \"eff_mhz\": %.0f}\n",
+         names[OP], threads, winstr / mean, ms, mean / (ms * 1e3));
+  return 0;
+}
+
+template <int OP> struct Loop { static int go(int sms, float* o, long long* c) {
+  if (run<OP>(sms, 512, o, c)) return 1; if (run<OP>(sms, 1024, o, c)) return 1; return Loop<OP + 1>::go(sms, o, c); } };
+template <> struct Loop<NOPS> { static int go(int, float*, long long*) { return 0; } };
+
+int main() {
+  cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+  int sms = p.multiProcessorCount;
+  printf("{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", p.name, sms, p.clockRate);
+  float* out; long long* cyc;
+  CK(cudaMalloc(&out, sizeof(float) * sms * 1024)); CK(cudaMalloc(&cyc, sizeof(long long) * 1024));
+  return Loop<0>::go(sms, out, cyc);
+}
