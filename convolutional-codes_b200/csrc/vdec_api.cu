@@ -1,0 +1,295 @@
+// vdec_api.cu — the C ABI of include/vdec.h: handle lifecycle, kernel selection, chunked launches
+// and the host-buffer pipeline.  No torch types, no CPU decode path: every compute entry point
+// either launches CUDA kernels or fails with -1.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "vdec_internal.h"
+
+namespace vd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (getenv("VDEC_QUIET") == nullptr) fprintf(stderr, "[vdec] %s\n", g_err);   // callers of the legacy API ignore returns
+}
+
+static size_t in_bytes_per_frame(const vdec* h) {
+    return h->cfg.metric == VDEC_HARD_U16 ? (size_t)h->geom.T : (size_t)h->geom.T * h->geom.M * sizeof(float);
+}
+
+}  // namespace vd
+
+// survivor scratch, one slot per concurrently running stream (0: decode_device, 1/2: host pipeline)
+struct vdec_scratch { uint32_t* p[3]; size_t bytes[3]; };
+
+// kept out of the public struct to keep vdec_internal.h small
+struct vdec_priv {
+    vdec base;
+    vdec_scratch sc;
+    size_t stage_frames;      // capacity of the host pipeline buffers, in frames
+};
+
+static vdec_priv* priv(vdec_t* h) { return reinterpret_cast<vdec_priv*>(h); }
+
+static int ensure_scratch(vdec_priv* p, int slot, uint32_t frames) {
+    vdec* h = &p->base;
+    vd::LaunchGeom g = h->geom;
+    g.nframes = frames;
+    const size_t need = h->regs ? h->regs->surv_bytes(g) : vd::generic_surv_bytes(g);
+    if (need <= p->sc.bytes[slot]) return 0;
+    if (p->sc.p[slot]) { VDEC_CUDA(cudaFree(p->sc.p[slot])); p->sc.p[slot] = nullptr; p->sc.bytes[slot] = 0; }
+    VDEC_CUDA(cudaMalloc(&p->sc.p[slot], need));
+    p->sc.bytes[slot] = need;
+    return 0;
+}
+
+static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframes, uint8_t* out_dev, int32_t* pm_dev,
+                     cudaStream_t st) {
+    vdec* h = &p->base;
+    const size_t ib = vd::in_bytes_per_frame(h);
+    uint64_t done = 0;
+    while (done < nframes) {
+        const uint32_t n = (uint32_t)((nframes - done < h->max_frames) ? (nframes - done) : h->max_frames);
+        if (ensure_scratch(p, slot, n) != 0) return -1;
+        vd::LaunchGeom g = h->geom;
+        g.nframes = n;
+        const void* in = static_cast<const uint8_t*>(in_dev) + done * ib;
+        uint8_t* out = out_dev + done * g.out_bytes;
+        int32_t* pm = pm_dev ? pm_dev + done : nullptr;
+        int rc;
+        if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
+        else rc = vd::generic_launch(g, h->cfg.metric, h->bfly_labels_dev, in, out, pm, p->sc.p[slot], st);
+        if (rc != 0) return -1;
+        h->launches += 1;
+        done += n;
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* vdec_last_error(void) { return vd::g_err; }
+
+int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
+    if (!out || !cfg) { vd::set_error("vdec_create: null argument"); return -1; }
+    *out = nullptr;
+    if (cfg->symlen_out < 1 || cfg->symlen_out > 3) { vd::set_error("symlen_out %u unsupported (1..3)", cfg->symlen_out); return -1; }
+    if (cfg->constr_len < 2 || cfg->constr_len > 15) { vd::set_error("constr_len %u unsupported (2..15)", cfg->constr_len); return -1; }
+    if (cfg->block_len < 1 || cfg->block_len > (1u << 24)) { vd::set_error("block_len %u unsupported", cfg->block_len); return -1; }
+    if (cfg->metric > VDEC_HARD_U16 || cfg->parity > VDEC_PARITY_LINEAR) { vd::set_error("bad metric/parity selector"); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        vd::set_error("no CUDA device: this library has no CPU path"); return -1;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { vd::set_error("device %d out of range (%d present)", cfg->device, ndev); return -1; }
+    VDEC_CUDA(cudaSetDevice(cfg->device));
+
+    vdec_priv* p = static_cast<vdec_priv*>(calloc(1, sizeof(vdec_priv)));
+    if (!p) { vd::set_error("out of host memory"); return -1; }
+    vdec* h = &p->base;
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    vd::LaunchGeom& g = h->geom;
+    g.K = cfg->constr_len; g.n = cfg->symlen_out; g.L = cfg->block_len;
+    g.S = 1u << (g.K - 1); g.T = g.L + g.K - 1; g.M = 1u << g.n;
+    g.out_bytes = (g.T + 7) / 8; g.nw = (g.S + 31) / 32; g.nframes = 0;
+
+    // trellis labels from the caller's polynomials (read now: the pointer is only borrowed, viterbi-decoder.c:169)
+    const bool quirk = cfg->parity == VDEC_PARITY_REF;
+    for (uint32_t s = 0; s < g.S; ++s)
+        for (uint32_t i = 0; i < 2; ++i)
+            h->labels_host[2 * s + i] = (uint8_t)vd::branch_label(g.K, g.n, cfg->polynomials, quirk, s, i);
+    uint32_t* bl = static_cast<uint32_t*>(malloc(sizeof(uint32_t) * (g.S / 2)));
+    if (!bl) { free(p); vd::set_error("out of host memory"); return -1; }
+    for (uint32_t m = 0; m < g.S / 2; ++m)
+        bl[m] = (uint32_t)h->labels_host[2 * (2 * m)] | ((uint32_t)h->labels_host[2 * (2 * m + 1)] << 8) |
+                ((uint32_t)h->labels_host[2 * (2 * m) + 1] << 16) | ((uint32_t)h->labels_host[2 * (2 * m + 1) + 1] << 24);
+    cudaError_t e = cudaMalloc(&h->labels_dev, 2 * g.S);
+    if (e == cudaSuccess) e = cudaMalloc(&h->bfly_labels_dev, sizeof(uint32_t) * (g.S / 2));
+    if (e == cudaSuccess) e = cudaMemcpy(h->labels_dev, h->labels_host, 2 * g.S, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->bfly_labels_dev, bl, sizeof(uint32_t) * (g.S / 2), cudaMemcpyHostToDevice);
+    free(bl);
+    if (e != cudaSuccess) { vd::set_error("label upload failed: %s", cudaGetErrorString(e)); vdec_destroy(h); return -1; }
+
+    h->regs = (cfg->flags & VDEC_FORCE_GENERIC) ? nullptr : vd::regs_find(g.K, g.n, cfg->metric, h->labels_host);
+    if (h->regs) {
+        snprintf(h->kernel_name, sizeof(h->kernel_name), "%s", h->regs->name);
+        h->max_frames = cfg->max_frames ? cfg->max_frames : (1u << 20);
+    } else {
+        snprintf(h->kernel_name, sizeof(h->kernel_name), "generic_%s<K%u n%u table-driven>",
+                 cfg->metric == VDEC_HARD_U16 ? "hard_u16" : "soft_f32", g.K, g.n);
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+        if (vd::generic_smem_bytes(g) > (size_t)max_smem) {
+            vd::set_error("K=%u needs %zu B shared memory per CTA, device offers %d", g.K, vd::generic_smem_bytes(g), max_smem);
+            vdec_destroy(h); return -1;
+        }
+        // bound the survivor scratch of one launch to ~4 GiB
+        const size_t per_frame = (size_t)g.T * g.nw * 4;
+        size_t cap = ((size_t)4 << 30) / per_frame;
+        if (cap < 1) cap = 1;
+        if (cap > (1u << 20)) cap = 1u << 20;
+        h->max_frames = cfg->max_frames ? cfg->max_frames : (uint32_t)cap;
+        if (h->max_frames > cap) h->max_frames = (uint32_t)cap;
+    }
+    *out = h;
+    return 0;
+}
+
+void vdec_destroy(vdec_t* h) {
+    if (!h) return;
+    vdec_priv* p = priv(h);
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 3; ++i) if (p->sc.p[i]) cudaFree(p->sc.p[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (h->dev_in[i]) cudaFree(h->dev_in[i]);
+        if (h->dev_out[i]) cudaFree(h->dev_out[i]);
+        if (h->dev_pm[i]) cudaFree(h->dev_pm[i]);
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    }
+    if (h->labels_dev) cudaFree(h->labels_dev);
+    if (h->bfly_labels_dev) cudaFree(h->bfly_labels_dev);
+    free(p);
+}
+
+uint32_t vdec_steps(const vdec_t* h) { return h->geom.T; }
+uint32_t vdec_states(const vdec_t* h) { return h->geom.S; }
+size_t vdec_in_bytes_per_frame(const vdec_t* h) { return vd::in_bytes_per_frame(h); }
+size_t vdec_out_bytes_per_frame(const vdec_t* h) { return h->geom.out_bytes; }
+const char* vdec_kernel_name(const vdec_t* h) { return h->kernel_name; }
+uint64_t vdec_launch_count(const vdec_t* h) { return h->launches; }
+
+int vdec_config_labels(const struct vdec_config* cfg, uint8_t* labels) {
+    if (!cfg || !labels) { vd::set_error("vdec_config_labels: null argument"); return -1; }
+    if (cfg->symlen_out < 1 || cfg->symlen_out > 3 || cfg->constr_len < 2 || cfg->constr_len > 15) {
+        vd::set_error("vdec_config_labels: unsupported code"); return -1;
+    }
+    const uint32_t S = 1u << (cfg->constr_len - 1);
+    for (uint32_t s = 0; s < S; ++s)
+        for (uint32_t i = 0; i < 2; ++i)
+            labels[2 * s + i] = (uint8_t)vd::branch_label(cfg->constr_len, cfg->symlen_out, cfg->polynomials,
+                                                          cfg->parity == VDEC_PARITY_REF, s, i);
+    return 0;
+}
+
+const char* vdec_config_kernel_name(const struct vdec_config* cfg) {
+    static thread_local char name[128];
+    uint8_t labels[2 * 16384];
+    if (vdec_config_labels(cfg, labels) != 0) return "";
+    const vd::RegsEntry* e = (cfg->flags & VDEC_FORCE_GENERIC) ? nullptr
+                             : vd::regs_find(cfg->constr_len, cfg->symlen_out, cfg->metric, labels);
+    if (e) snprintf(name, sizeof(name), "%s", e->name);
+    else snprintf(name, sizeof(name), "generic_%s<K%u n%u table-driven>", cfg->metric == VDEC_HARD_U16 ? "hard_u16" : "soft_f32",
+                  cfg->constr_len, cfg->symlen_out);
+    return name;
+}
+
+int vdec_labels(const vdec_t* h, uint8_t* labels) {
+    if (!h || !labels) { vd::set_error("vdec_labels: null argument"); return -1; }
+    memcpy(labels, h->labels_host, 2 * h->geom.S);
+    return 0;
+}
+
+int vdec_decode_device(vdec_t* h, const void* in_dev, uint64_t nframes, uint8_t* out_dev, int32_t* path_metric_dev,
+                       void* cuda_stream) {
+    if (!h || (nframes && (!in_dev || !out_dev))) { vd::set_error("vdec_decode_device: null argument"); return -1; }
+    if (nframes == 0) return 0;
+    VDEC_CUDA(cudaSetDevice(h->device));
+    return decode_on(priv(h), 0, in_dev, nframes, out_dev, path_metric_dev, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vdec_decode_host(vdec_t* h, const void* in_host, uint64_t nframes, uint8_t* out_host, int32_t* path_metric_host) {
+    if (!h || (nframes && (!in_host || !out_host))) { vd::set_error("vdec_decode_host: null argument"); return -1; }
+    if (nframes == 0) return 0;
+    vdec_priv* p = priv(h);
+    VDEC_CUDA(cudaSetDevice(h->device));
+    const size_t ib = vd::in_bytes_per_frame(h), ob = h->geom.out_bytes;
+    // pipeline stage size: ~64 MiB of input, at least 1 frame, at most what is asked for
+    size_t chunk = ((size_t)64 << 20) / ib;
+    if (chunk < 1) chunk = 1;
+    if (chunk > h->max_frames) chunk = h->max_frames;
+    if (chunk > nframes) chunk = nframes;
+    if (chunk > p->stage_frames) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->dev_in[i]) { cudaFree(h->dev_in[i]); h->dev_in[i] = nullptr; }
+            if (h->dev_out[i]) { cudaFree(h->dev_out[i]); h->dev_out[i] = nullptr; }
+            if (h->dev_pm[i]) { cudaFree(h->dev_pm[i]); h->dev_pm[i] = nullptr; }
+        }
+        p->stage_frames = 0;
+        for (int i = 0; i < 2; ++i) {
+            if (!h->streams[i]) VDEC_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+            VDEC_CUDA(cudaMalloc(&h->dev_in[i], chunk * ib));
+            VDEC_CUDA(cudaMalloc(&h->dev_out[i], chunk * ob));
+            VDEC_CUDA(cudaMalloc(&h->dev_pm[i], chunk * sizeof(int32_t)));
+        }
+        p->stage_frames = chunk;
+    }
+    const bool want_pm = path_metric_host != nullptr && h->cfg.metric == VDEC_HARD_U16;
+    uint64_t done = 0;
+    int stage = 0;
+    while (done < nframes) {
+        const uint64_t n = (nframes - done < chunk) ? (nframes - done) : chunk;
+        cudaStream_t st = h->streams[stage];
+        // the stage's previous D2H must have drained before its buffers are reused: stream order does that
+        VDEC_CUDA(cudaMemcpyAsync(h->dev_in[stage], static_cast<const uint8_t*>(in_host) + done * ib, n * ib,
+                                  cudaMemcpyHostToDevice, st));
+        if (decode_on(p, 1 + stage, h->dev_in[stage], n, h->dev_out[stage], want_pm ? h->dev_pm[stage] : nullptr, st) != 0) return -1;
+        VDEC_CUDA(cudaMemcpyAsync(out_host + done * ob, h->dev_out[stage], n * ob, cudaMemcpyDeviceToHost, st));
+        if (want_pm)
+            VDEC_CUDA(cudaMemcpyAsync(path_metric_host + done, h->dev_pm[stage], n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        done += n;
+        stage ^= 1;
+    }
+    VDEC_CUDA(cudaStreamSynchronize(h->streams[0]));
+    VDEC_CUDA(cudaStreamSynchronize(h->streams[1]));
+    if (path_metric_host != nullptr && !want_pm) memset(path_metric_host, 0, nframes * sizeof(int32_t));
+    return 0;
+}
+
+int vdec_sync(vdec_t* h) {
+    if (!h) return -1;
+    VDEC_CUDA(cudaSetDevice(h->device));
+    VDEC_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+int vdec_count_errors_device(vdec_t* h, const uint8_t* decoded_dev, const uint8_t* payload_dev, uint64_t nframes,
+                             uint64_t* counters_dev, void* cuda_stream) {
+    if (!h || !decoded_dev || !payload_dev || !counters_dev) { vd::set_error("vdec_count_errors_device: null argument"); return -1; }
+    VDEC_CUDA(cudaSetDevice(h->device));
+    h->launches += 1;
+    return vd::count_errors_launch(decoded_dev, payload_dev, nframes, h->geom.L, h->geom.out_bytes, counters_dev,
+                                   static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vdec_demap_device(uint32_t symlen_out, const float* iq_dev, uint64_t nsym, float* metrics_dev, void* cuda_stream) {
+    if (!iq_dev || !metrics_dev) { vd::set_error("vdec_demap_device: null argument"); return -1; }
+    return vd::demap_launch(symlen_out, iq_dev, nsym, metrics_dev, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vdec_synth_awgn_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uint64_t seed, float sigma,
+                           uint8_t* payload_dev, float* metrics_dev, float* iq_dev, void* cuda_stream) {
+    if (!h || !payload_dev || !metrics_dev) { vd::set_error("vdec_synth_awgn_device: null argument"); return -1; }
+    VDEC_CUDA(cudaSetDevice(h->device));
+    h->launches += 2;
+    return vd::synth_awgn_launch(h->geom, h->labels_dev, nframes, first_frame, seed, sigma, payload_dev, metrics_dev, iq_dev,
+                                 static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vdec_synth_bsc_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uint64_t seed, uint32_t crossover_ppm,
+                          uint8_t* payload_dev, uint8_t* symbols_dev, void* cuda_stream) {
+    if (!h || !payload_dev || !symbols_dev) { vd::set_error("vdec_synth_bsc_device: null argument"); return -1; }
+    VDEC_CUDA(cudaSetDevice(h->device));
+    h->launches += 2;
+    return vd::synth_bsc_launch(h->geom, h->labels_dev, nframes, first_frame, seed, crossover_ppm, payload_dev, symbols_dev,
+                                static_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// vdec_internal.h — shared between the translation units of libvdec.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/vdec.h"
+#include "vdec_labels.h"
+
+namespace vd {
+
+void set_error(const char* fmt, ...);
+
+#define VDEC_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            ::vd::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return -1;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+// Geometry of one decode launch, passed by value to the kernels.
+struct LaunchGeom {
+    uint32_t K, n, L, S, T, M;
+    uint32_t out_bytes;      // (T+7)/8
+    uint32_t nw;             // survivor words (32 decisions each) per trellis step
+    uint32_t nframes;        // frames in this launch
+};
+
+// ---- code-specialised register kernels (vdec_regs.cu) -------------------------------------
+// One thread per frame, all S <= 64 path metrics in registers, labels are compile-time
+// constants.  An entry serves a request when its label table equals the requested code's.
+struct RegsEntry {
+    const char* name;
+    uint32_t K, n, metric;
+    uint8_t labels[128];                       // [S][2]
+    int (*launch)(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric,
+                  uint32_t* surv, cudaStream_t st);
+    size_t (*surv_bytes)(const LaunchGeom& g);
+};
+const RegsEntry* regs_find(uint32_t K, uint32_t n, uint32_t metric, const uint8_t* labels);
+int regs_count();
+const RegsEntry* regs_at(int i);
+
+// ---- generic table-driven kernels (vdec_generic.cu) ----------------------------------------
+// One CTA per frame, path metrics in shared memory, labels from a device table; any K <= 15.
+int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
+                   uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st);
+size_t generic_surv_bytes(const LaunchGeom& g);
+size_t generic_smem_bytes(const LaunchGeom& g);
+
+// ---- aux kernels (vdec_synth.cu) ---------------------------------------------------------------
+int count_errors_launch(const uint8_t* dec, const uint8_t* payload, uint64_t nframes, uint32_t L,
+                        uint32_t out_bytes, uint64_t* counters, cudaStream_t st);
+int demap_launch(uint32_t n, const float* iq, uint64_t nsym, float* metrics, cudaStream_t st);
+int synth_awgn_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t nframes, uint64_t first_frame,
+                      uint64_t seed, float sigma, uint8_t* payload, float* metrics, float* iq, cudaStream_t st);
+int synth_bsc_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t nframes, uint64_t first_frame,
+                     uint64_t seed, uint32_t crossover_ppm, uint8_t* payload, uint8_t* symbols, cudaStream_t st);
+
+}  // namespace vd
+
+// The opaque handle of include/vdec.h
+struct vdec {
+    vdec_config cfg;
+    vd::LaunchGeom geom;           // nframes filled per launch
+    int device;
+    uint32_t max_frames;             // frames per launch
+    uint8_t labels_host[2 * 32768];  // [S][2], K <= 15 -> S <= 16384
+    uint8_t* labels_dev;             // [S][2]
+    uint32_t* bfly_labels_dev;       // [S/2] packed l00 | l01<<8 | l10<<16 | l11<<24
+    const vd::RegsEntry* regs;     // non-null => specialised kernel
+    uint32_t* surv;                  // survivor scratch
+    size_t surv_bytes;
+    // host-buffer pipeline (vdec_decode_host)
+    cudaStream_t streams[2];
+    void* pin_in[2]; uint8_t* pin_out[2]; int32_t* pin_pm[2];
+    void* dev_in[2]; uint8_t* dev_out[2]; int32_t* dev_pm[2];
+    uint32_t host_chunk;             // frames per pipeline stage
+    uint64_t launches;
+    char kernel_name[128];
+};

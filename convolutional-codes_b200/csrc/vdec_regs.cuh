@@ -1,0 +1,271 @@
+// vdec_regs.cuh — code-specialised Viterbi kernel: ONE THREAD PER FRAME.
+//
+// Replaces receive_symbol()/traceback() of the reference decoders
+// (AWGN-channel/viterbi-decoder.c:71-90,108-141; binary-symmetric-channel/viterbi-decoder.c:75-96,
+// 114-150) for codes with S = 2^(K-1) <= 64 states.
+//
+// Layout of the computation
+//   * all S path metrics of a frame live in registers of one thread; a warp decodes 32 frames,
+//     so no shuffles, no shared-memory traffic and no divergence in the ACS loop;
+//   * the trellis butterfly {2m,2m+1} -> {m, m+S/2} is done IN PLACE: new[m] overwrites the
+//     register of old[2m], new[m+S/2] that of old[2m+1].  After p steps logical state s sits in
+//     physical register rotl(s, p) (rotation over the K-1 state bits), so unrolling K-1 steps
+//     returns to the identity and the loop needs no register moves;
+//   * branch labels are compile-time constants (template parameter CodeDef), so `bm[label]`
+//     is a register operand: per state update the kernel issues 2 adds, 1 compare, 1 select and
+//     1 predicated OR that drops the decision bit into its survivor word;
+//   * decisions: 1 bit per state per step (the reference stores a 4-byte struct,
+//     viterbi-decoder.c:12-15), written coalesced as [warp][step][lane] words to an HBM scratch;
+//   * tie rule = reference: strict '<' with the even predecessor visited first => a tie keeps
+//     predecessor 2m, decision bit 0 (viterbi-decoder.c:115-126); final state = lowest-index
+//     argmin over all states (:72-79); every one of the T steps allows both inputs;
+//   * traceback re-reads the scratch (coalesced), emits all T bits MSB-first (:81-89) through a
+//     shared-memory staging tile so the global write of the warp's 32 output rows is contiguous.
+//
+// Soft metrics are fp32 and every candidate is `pm + bm` exactly as the reference computes it
+// (:121), so the result is bit-identical, not approximately equal.  Inputs are assumed finite
+// and NaN-free (the demapper guarantees it).
+#pragma once
+#include <type_traits>
+#include <utility>
+
+#include "vdec_internal.h"
+
+namespace vd {
+
+template <int K_, int N_, uint64_t P0_, uint64_t P1_, uint64_t P2_, bool REF_>
+struct CodeDef {
+    static constexpr int K = K_, N = N_, B = K_ - 1, S = 1 << (K_ - 1), M = 1 << N_;
+    static constexpr int NW = (S + 31) / 32;
+    VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {
+        const uint64_t p[3] = {P0_, P1_, P2_};
+        return branch_label(K_, N_, p, REF_, s, i);
+    }
+};
+
+constexpr int kRegsThreads = 128;
+
+// compile-time loop: f(integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
+// ---- metric policies -----------------------------------------------------------------------
+struct SoftF32 {
+    using T = float;
+    using In = float;
+    static constexpr uint32_t kMetric = VDEC_SOFT_F32;
+    __device__ static __forceinline__ T init_rest() { return __int_as_float(0x7f800000); }   // +INF, :215-218
+    // dst = min(ce, co), decision bit set iff co < ce  (strict: tie -> even predecessor)
+    __device__ static __forceinline__ void acs(T& dst, T pe, T po, T be, T bo, uint32_t& dw, uint32_t bit) {
+        const float ce = __fadd_rn(pe, be), co = __fadd_rn(po, bo);
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.lt.f32 p, %3, %2;\n\t"
+            "selp.f32 %0, %3, %2, p;\n\t"
+            "@p or.b32 %1, %1, %4;\n\t}"
+            : "=f"(dst), "+r"(dw) : "f"(ce), "f"(co), "r"(bit));
+    }
+    __device__ static __forceinline__ bool less(T a, T b) { return a < b; }
+    __device__ static __forceinline__ int32_t to_path_metric(T) { return 0; }
+    // branch metrics of one step: the M demapper distances, as loaded
+    template <int M>
+    __device__ static __forceinline__ void load(const In* __restrict__ p, T (&bm)[M]) {
+        if constexpr (M == 2) { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); bm[0] = v.x; bm[1] = v.y; }
+        else {
+#pragma unroll
+            for (int i = 0; i < M / 4; ++i) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+                bm[4 * i] = v.x; bm[4 * i + 1] = v.y; bm[4 * i + 2] = v.z; bm[4 * i + 3] = v.w;
+            }
+        }
+    }
+    template <int M> VDEC_HD static constexpr size_t step_elems() { return M; }
+};
+
+struct HardU16 {
+    using T = uint32_t;      // uint16 semantics (clamp at 0xFF00) carried in 32-bit registers
+    using In = uint8_t;
+    static constexpr uint32_t kMetric = VDEC_HARD_U16;
+    __device__ static __forceinline__ T init_rest() { return 0xFF00u; }                      // :225-228
+    __device__ static __forceinline__ void acs(T& dst, T pe, T po, T be, T bo, uint32_t& dw, uint32_t bit) {
+        const uint32_t ce = min(pe + be, 0xFF00u), co = min(po + bo, 0xFF00u);                  // :127-130
+        const bool d = co < ce;
+        dst = d ? co : ce;
+        if (d) dw |= bit;
+    }
+    __device__ static __forceinline__ bool less(T a, T b) { return a < b; }
+    __device__ static __forceinline__ int32_t to_path_metric(T v) { return (int32_t)v; }
+    // branch metrics of one step: Hamming distance of every possible label to the received symbol (:69-72)
+    template <int M>
+    __device__ static __forceinline__ void load(const In* __restrict__ p, T (&bm)[M]) {
+        const uint32_t r = __ldg(p) & (M - 1);                                                 // :235-237
+#pragma unroll
+        for (int e = 0; e < M; ++e) bm[e] = __popc(e ^ r);
+    }
+    template <int M> VDEC_HD static constexpr size_t step_elems() { return 1; }
+};
+
+// ---- one trellis step at rotation phase PH ---------------------------------------------------
+template <class CD, class MP, int PH>
+__device__ __forceinline__ void acs_step(typename MP::T (&r)[CD::S], const typename MP::T (&bm)[CD::M],
+                                         uint32_t (&dw)[CD::NW]) {
+    constexpr int B = CD::B, S = CD::S, PB = PH % B;
+#pragma unroll
+    for (int w = 0; w < CD::NW; ++w) dw[w] = 0;
+#pragma unroll
+    for (int a = 0; a < S; ++a) {
+        if ((a >> PB) & 1) continue;                 // a holds the even state of a butterfly
+        const int b = a | (1 << PB);                 // partner: the odd state
+        const uint32_t u = rotr_bits(a, PH, B);      // logical 2m
+        const uint32_t v = u + 1;                    // logical 2m+1
+        const uint32_t j0 = u >> 1, j1 = j0 + S / 2; // successors (input 0 / input 1)
+        const typename MP::T pe = r[a], po = r[b];
+        MP::acs(r[a], pe, po, bm[CD::label(u, 0)], bm[CD::label(v, 0)], dw[j0 >> 5], 1u << (j0 & 31));
+        MP::acs(r[b], pe, po, bm[CD::label(u, 1)], bm[CD::label(v, 1)], dw[j1 >> 5], 1u << (j1 & 31));
+    }
+}
+
+template <int NW> struct SurvWord;
+template <> struct SurvWord<1> { using type = uint32_t; };
+template <> struct SurvWord<2> { using type = uint2; };
+
+template <int NW>
+__device__ __forceinline__ void surv_store(uint32_t* p, const uint32_t (&dw)[NW]) {
+    if constexpr (NW == 1) *p = dw[0];
+    else *reinterpret_cast<uint2*>(p) = make_uint2(dw[0], dw[1]);
+}
+
+// lowest-index argmin over LOGICAL states when the registers are in rotation phase PH
+template <class CD, class MP, int PH>
+__device__ __forceinline__ void argmin_phase(const typename MP::T (&r)[CD::S], typename MP::T& best, uint32_t& idx) {
+    best = MP::init_rest(); idx = 0;                                                           // :72-73
+#pragma unroll
+    for (int s = 0; s < CD::S; ++s) {
+        const typename MP::T v = r[rotl_bits(s, PH, CD::B)];
+        if (MP::less(v, best)) { best = v; idx = s; }                                          // :75-78
+    }
+}
+
+template <class CD, class MP>
+__global__ void __launch_bounds__(kRegsThreads)
+vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
+                uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words) {
+    using MT = typename MP::T;
+    constexpr int S = CD::S, B = CD::B, M = CD::M, NW = CD::NW;
+    extern __shared__ uint32_t s_stage[];            // [threads][stage_words] output staging
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t f = blockIdx.x * kRegsThreads + tid;
+    const bool live = f < nframes;
+    const uint32_t fr = live ? f : nframes - 1;      // dead lanes shadow the last frame, store nothing
+    const size_t step_elems = MP::template step_elems<M>();
+    const typename MP::In* src = in + (size_t)fr * T * step_elems;
+    // survivor scratch: [global warp][step][lane][NW]
+    uint32_t* sv = surv + ((size_t)(f >> 5) * T * 32 + lane) * NW;
+
+    MT r[S];
+    r[0] = 0;                                        // decoder_reset: state 0 starts at metric 0 (:215)
+#pragma unroll
+    for (int s = 1; s < S; ++s) r[s] = MP::init_rest();
+
+    uint32_t dw[NW];
+    MT bm[M], bn[M];
+    MP::template load<M>(src, bm);
+
+    // ---- forward pass: full periods of B steps, then the T % B remainder --------------------
+    uint32_t t = 0;
+    for (; t + B <= T; t += B) {
+        static_for<0, B>([&](auto phc) {
+            constexpr int PH = decltype(phc)::value;
+            const uint32_t tn = min(t + PH + 1, T - 1);
+            MP::template load<M>(src + (size_t)tn * step_elems, bn);      // one step of lookahead
+            acs_step<CD, MP, PH>(r, bm, dw);
+            if (live) surv_store<NW>(sv + (size_t)(t + PH) * 32 * NW, dw);
+#pragma unroll
+            for (int i = 0; i < M; ++i) bm[i] = bn[i];
+        });
+    }
+    const uint32_t rem = T - t;                       // 0 .. B-1, warp-uniform
+    static_for<0, B - 1>([&](auto phc) {
+        constexpr int PH = decltype(phc)::value;
+        if (PH < (int)rem) {
+            const uint32_t tn = min(t + PH + 1, T - 1);
+            MP::template load<M>(src + (size_t)tn * step_elems, bn);
+            acs_step<CD, MP, PH>(r, bm, dw);
+            if (live) surv_store<NW>(sv + (size_t)(t + PH) * 32 * NW, dw);
+#pragma unroll
+            for (int i = 0; i < M; ++i) bm[i] = bn[i];
+        }
+    });
+
+    // ---- final state: lowest-index argmin over logical states (:72-79) ----------------------
+    MT best = MP::init_rest(); uint32_t cur = 0;
+    static_for<0, B>([&](auto phc) {
+        constexpr int PH = decltype(phc)::value;
+        if (PH == (int)rem) argmin_phase<CD, MP, PH>(r, best, cur);
+    });
+    if (live && path_metric != nullptr) path_metric[f] = MP::to_path_metric(best);            // :94, :143
+
+    // ---- traceback (:81-89): decision of state `cur` at step tt, decoded bit = MSB of cur -----
+    uint32_t* stage = s_stage + (size_t)tid * stage_words;
+    uint32_t acc = 0;
+    if (live)
+    for (int tt = (int)T - 1; tt >= 0; --tt) {
+        uint32_t word;
+        if constexpr (NW == 1) word = sv[(size_t)tt * 32];
+        else word = sv[(size_t)tt * 64 + (cur >> 5)];
+        const uint32_t d = (word >> (cur & 31)) & 1u;
+        acc |= (cur >> (B - 1)) << (31 - (tt & 31));          // bit tt -> byte tt/8, bit 7-(tt%8)  (:88)
+        cur = ((cur << 1) & (S - 1)) | d;                      // predecessor (:86)
+        if ((tt & 31) == 0) { stage[tt >> 5] = __byte_perm(acc, 0, 0x0123); acc = 0; }
+    }
+    __syncwarp();
+
+    // ---- write the warp's 32 output rows (contiguous in global memory) ----------------------
+    const uint32_t wbase = (blockIdx.x * kRegsThreads + (tid & ~31u));     // first frame of this warp
+    if (wbase < nframes) {
+        const uint32_t rows = min(32u, nframes - wbase);
+        const uint32_t total = rows * out_bytes;
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_stage + (size_t)(tid & ~31u) * stage_words);
+        uint8_t* dst = out + (size_t)wbase * out_bytes;
+        uint32_t row = 0, col = lane;
+        while (col >= out_bytes) { col -= out_bytes; ++row; }
+        for (uint32_t i = lane; i < total; i += 32) {
+            dst[i] = sb[(size_t)row * stage_words * 4 + col];
+            col += 32;
+            while (col >= out_bytes) { col -= out_bytes; ++row; }
+        }
+    }
+}
+
+template <class CD, class MP>
+int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
+    uint32_t stage_words = (g.out_bytes + 3) / 4;
+    if ((stage_words & 1) == 0) ++stage_words;                 // odd stride: conflict-free column writes
+    const size_t smem = (size_t)kRegsThreads * stage_words * 4;
+    auto kern = vit_regs_kernel<CD, MP>;
+    if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t blocks = (g.nframes + kRegsThreads - 1) / kRegsThreads;
+    kern<<<blocks, kRegsThreads, smem, st>>>(static_cast<const typename MP::In*>(in), out, path_metric, surv,
+                                              g.nframes, g.T, g.out_bytes, stage_words);
+    VDEC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <class CD>
+size_t regs_surv_bytes(const LaunchGeom& g) {
+    return (size_t)((g.nframes + 31) / 32) * g.T * 32 * CD::NW * sizeof(uint32_t);
+}
+
+template <class CD, class MP>
+RegsEntry make_regs_entry(const char* name) {
+    RegsEntry e{};
+    e.name = name; e.K = CD::K; e.n = CD::N; e.metric = MP::kMetric;
+    for (int s = 0; s < CD::S; ++s) { e.labels[2 * s] = (uint8_t)CD::label(s, 0); e.labels[2 * s + 1] = (uint8_t)CD::label(s, 1); }
+    e.launch = &regs_launch<CD, MP>;
+    e.surv_bytes = &regs_surv_bytes<CD>;
+    return e;
+}
+
+}  // namespace vd

@@ -1,0 +1,130 @@
+/*
+ * vdec.h — batched C ABI of the B200-native Viterbi decoder.
+ *
+ * This is the drop-in boundary for the Viterbi hot path of
+ * thomas-emig/convolutional-codes.  The reference decodes one frame per
+ * `struct decoder` through six functions (AWGN-channel/include/decoder.h:17-26,
+ * binary-symmetric-channel/include/decoder.h:17-26); that legacy surface is
+ * re-exported unchanged by libvdec_awgn.so / libvdec_bsc.so
+ * (include/vdec_legacy_awgn.h, include/vdec_legacy_bsc.h).  The legacy ABI is
+ * one-frame-per-call and 8-bit sized, so throughput goes through the batched
+ * entry points below: same code description, same input and output formats,
+ * `nframes` independent frames per call.
+ *
+ * Formats (identical to what the reference decoder consumes / produces):
+ *   soft input   float32 [nframes][T][M]   M = 2^n demapper distances per trellis step
+ *                                          (common/demapper.c:66-70 -> viterbi-decoder.c:224-236)
+ *   hard input   uint8   [nframes][T]      one n-bit symbol per step in the low bits
+ *                                          (binary-symmetric-channel/viterbi-decoder.c:234-243)
+ *   output       uint8   [nframes][(T+7)/8] decoded bits MSB-first, ALL T = L+K-1 bits
+ *                                          (tail included, as viterbi-decoder.c:81-89 writes them)
+ *   path metric  int32   [nframes]         hard decoder only: final minimum metric
+ *                                          (binary-symmetric-channel/viterbi-decoder.c:75-96,143)
+ *
+ * All functions return 0 on success and -1 on failure, as the reference API does;
+ * vdec_last_error() gives the reason.  There is no CPU fallback: without a CUDA
+ * device every compute entry point fails.
+ */
+#ifndef VDEC_H
+#define VDEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDEC_MAX_POLY 8
+
+enum vdec_metric {
+    VDEC_SOFT_F32 = 0,   /* AWGN-channel/viterbi-decoder.c: float path metrics, +INF = unreachable */
+    VDEC_HARD_U16 = 1    /* binary-symmetric-channel/viterbi-decoder.c: uint16 metrics clamped at 0xFF00 */
+};
+
+enum vdec_parity {
+    VDEC_PARITY_REF = 0,     /* trellis labels exactly as the reference's `(0x6996 >> val) & 1`
+                                evaluates on x86-64 (viterbi-decoder.c:52-57, encoder.c:95-100) */
+    VDEC_PARITY_LINEAR = 1   /* true GF(2) parity: the textbook code for the same polynomials */
+};
+
+enum vdec_flags {
+    VDEC_FORCE_GENERIC = 1u  /* never pick a code-specialised kernel (testing) */
+};
+
+/* Mirrors the fields of `struct code_param` the decoders read (common/include/code.h:9-19),
+ * widened to 32 bits.  polynomials[] are left-aligned: bit 63 taps the newest input bit
+ * (common/codebook.c:14-17). */
+struct vdec_config {
+    uint32_t symlen_out;               /* n, 1..3 */
+    uint32_t constr_len;               /* K, 2..15 */
+    uint32_t block_len;                /* L >= 1 */
+    uint32_t metric;                   /* enum vdec_metric */
+    uint32_t parity;                   /* enum vdec_parity */
+    uint32_t flags;                    /* enum vdec_flags */
+    int32_t  device;                   /* CUDA device ordinal */
+    uint32_t max_frames;               /* frames per kernel launch; 0 = default */
+    uint64_t polynomials[VDEC_MAX_POLY];
+};
+
+typedef struct vdec vdec_t;
+
+/* lifecycle — replaces decoder_create + decoder_init (viterbi-decoder.c:144-150,168-206) */
+int         vdec_create(vdec_t** out, const struct vdec_config* cfg);
+void        vdec_destroy(vdec_t* h);
+const char* vdec_last_error(void);
+
+/* host-only helpers (no device needed): the label table / kernel family a config would get */
+int         vdec_config_labels(const struct vdec_config* cfg, uint8_t* labels /* [2^(K-1)][2] */);
+const char* vdec_config_kernel_name(const struct vdec_config* cfg);
+
+/* geometry */
+uint32_t    vdec_steps(const vdec_t* h);             /* T = L + K - 1 */
+uint32_t    vdec_states(const vdec_t* h);            /* S = 2^(K-1) */
+size_t      vdec_in_bytes_per_frame(const vdec_t* h);
+size_t      vdec_out_bytes_per_frame(const vdec_t* h);
+const char* vdec_kernel_name(const vdec_t* h);       /* which CUDA kernel family serves this code */
+/* trellis labels: labels[2*s+i] = expected symbol for (state s, input i) (viterbi-decoder.c:45-63) */
+int         vdec_labels(const vdec_t* h, uint8_t* labels);
+
+/* decode `nframes` frames; buffers in device memory, asynchronous on `cuda_stream`
+ * (a cudaStream_t, NULL = legacy default stream).  path_metric_dev may be NULL. */
+int vdec_decode_device(vdec_t* h, const void* in_dev, uint64_t nframes, uint8_t* out_dev,
+                       int32_t* path_metric_dev, void* cuda_stream);
+/* same with HOST buffers: H2D, kernels, D2H, synchronous (pipelined in chunks).
+ * This is the call a reference maintainer binds; the legacy shims use it. */
+int vdec_decode_host(vdec_t* h, const void* in_host, uint64_t nframes, uint8_t* out_host,
+                     int32_t* path_metric_host);
+int vdec_sync(vdec_t* h);
+/* number of this library's kernels launched through `h` so far */
+uint64_t vdec_launch_count(const vdec_t* h);
+
+/* ---- the stages either side of the decoder ("next") ---------------------- */
+
+/* error counting of the drivers' output callbacks (AWGN-channel/main.c:129-141):
+ * counters_dev[0] += bits compared (nframes*L), [1] += bit errors, [2] += frames with >= 1 error.
+ * decoded rows are vdec_out_bytes_per_frame() apart, payload rows (L+7)/8. */
+int vdec_count_errors_device(vdec_t* h, const uint8_t* decoded_dev, const uint8_t* payload_dev,
+                             uint64_t nframes, uint64_t* counters_dev, void* cuda_stream);
+
+/* soft demapper, bit-exact to common/demapper.c:43-45,66-70: iq [nsym][2] -> metrics [nsym][2^n] */
+int vdec_demap_device(uint32_t symlen_out, const float* iq_dev, uint64_t nsym, float* metrics_dev,
+                      void* cuda_stream);
+
+/* GPU-resident synthetic link for frames [first_frame, first_frame+nframes): counter-based
+ * random payload -> encoder (encoder.c:84-119) -> mapper (mapper.c:54-71) -> AWGN of standard
+ * deviation `sigma` per real dimension (main.c:100-102) -> demapper.  Random numbers depend only
+ * on (seed, global frame index, step), so results do not depend on how frames are sharded.
+ * payload_dev [nframes][(L+7)/8]; metrics_dev [nframes][T][M]; iq_dev (optional) [nframes][T][2]. */
+int vdec_synth_awgn_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uint64_t seed, float sigma,
+                           uint8_t* payload_dev, float* metrics_dev, float* iq_dev, void* cuda_stream);
+/* binary symmetric channel: each coded bit flipped with probability crossover_ppm/1e6
+ * (binary-symmetric-channel/main.c:62-68).  symbols_dev [nframes][T]. */
+int vdec_synth_bsc_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uint64_t seed,
+                          uint32_t crossover_ppm, uint8_t* payload_dev, uint8_t* symbols_dev,
+                          void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDEC_H */

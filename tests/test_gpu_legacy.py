@@ -1,0 +1,143 @@
+"""GPU: the reference's six-function plugin ABI served by the shim libraries — the same call script
+is run against libvdec_{awgn,bsc}.so and (when built) against the compiled reference objects."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_hard_inputs, make_soft_inputs, ocode
+
+pytestmark = pytest.mark.gpu
+
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _targets(kind):
+    t = [None]
+    p = os.path.join(REFDIR, f"libref_{kind}.so")
+    if os.path.exists(p):
+        t.append(p)
+    return t
+
+
+@pytest.mark.parametrize("idx", [0, 3, 5])
+def test_awgn_per_symbol_calls(cc, orc, idx):
+    """AWGN driver pattern: one trellis step (M floats) per decoder_input call (main.c:108-116)"""
+    code = cc.get_code(idx)
+    _, met = make_soft_inputs(orc, ocode(code), 6, 0.5, seed=idx)
+    exp = orc.decode_soft(ocode(code), met)
+    for lib in _targets("awgn"):
+        d = cc.LegacyDecoder("awgn", lib)
+        assert d.init(code) == 0
+        d.register_callback()
+        for f in range(6):
+            for t in range(code.T):
+                before = len(d.frames)
+                assert d.input(met[f, t]) == 0
+                # the callback fires synchronously inside the call that delivers step T
+                assert len(d.frames) == before + (1 if t == code.T - 1 else 0)
+        got = np.frombuffer(b"".join(fr[0] for fr in d.frames), np.uint8).reshape(6, code.out_bytes)
+        assert np.array_equal(got, exp) and all(fr[1] == code.L for fr in d.frames)
+        d.destroy()
+        assert not d.obj                                              # destroy NULLs the caller's pointer
+
+
+def test_awgn_multi_symbol_calls_bad_len_reset_reinit(cc, orc):
+    code = cc.get_code(0)
+    _, met = make_soft_inputs(orc, ocode(code), 3, 0.5, seed=11)
+    exp = orc.decode_soft(ocode(code), met)
+    for lib in _targets("awgn"):
+        d = cc.LegacyDecoder("awgn", lib)
+        assert d.init(code) == 0
+        d.register_callback()
+        assert d.input(np.zeros(5, np.float32)) == -1                 # len % 2^n != 0 (viterbi-decoder.c:225-228)
+        flat = met[0].reshape(-1)
+        for off in range(0, flat.size, 28):                           # 7 steps per call
+            assert d.input(flat[off:off + 28]) == 0
+        assert len(d.frames) == 1
+        # mid-frame reset aborts the frame (:212-222)
+        assert d.input(met[1, :10].reshape(-1)) == 0
+        d.reset()
+        for t in range(code.T):
+            d.input(met[1, t])
+        assert len(d.frames) == 2
+        # re-init with another code, callback kept
+        code5 = cc.get_code(5)
+        _, met5 = make_soft_inputs(orc, ocode(code5), 1, 0.5, seed=12)
+        assert d.init(code5) == 0
+        for t in range(code5.T):
+            d.input(met5[0, t])
+        assert len(d.frames) == 3
+        assert np.array_equal(np.frombuffer(d.frames[0][0], np.uint8), exp[0])
+        assert np.array_equal(np.frombuffer(d.frames[1][0], np.uint8), exp[1])
+        assert np.array_equal(np.frombuffer(d.frames[2][0], np.uint8), orc.decode_soft(ocode(code5), met5)[0])
+        d.destroy()
+
+
+def test_awgn_null_callback_and_ownership_transfer(cc, orc):
+    code = cc.get_code(0)
+    _, met = make_soft_inputs(orc, ocode(code), 2, 0.5, seed=21)
+    exp = orc.decode_soft(ocode(code), met)
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+    for lib in _targets("awgn"):
+        d = cc.LegacyDecoder("awgn", lib)
+        assert d.init(code) == 0
+        for t in range(code.T):                                       # no callback registered: treated as -1
+            assert d.input(met[0, t]) == 0
+        # callback returns 0: the callee owns the malloc'd buffer and must free it (:97-104)
+        taken = []
+        CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint8, ctypes.c_void_p)
+
+        def cb(data, ln, ud):
+            taken.append((data, bytes((ctypes.c_uint8 * code.out_bytes).from_address(data))))
+            return 0
+        keep = CB(cb)
+        d.lib.decoder_register_callback(d.obj, ctypes.cast(keep, ctypes.c_void_p))
+        for f in range(2):
+            for t in range(code.T):
+                assert d.input(met[f, t]) == 0
+        assert len(taken) == 2 and taken[0][0] != taken[1][0]
+        for f, (ptr, data) in enumerate(taken):
+            assert np.array_equal(np.frombuffer(data, np.uint8), exp[f])
+            libc.free(ptr)
+        d.destroy()
+
+
+@pytest.mark.parametrize("idx", [0, 1, 5])
+def test_bsc_whole_frame_calls(cc, orc, idx):
+    """BSC driver pattern: T symbol bytes in one call, callback carries the path metric (main.c:70,74)"""
+    code = cc.get_code(idx)
+    _, sym = make_hard_inputs(orc, ocode(code), 8, 0.06, seed=idx)
+    exp, exp_pm = orc.decode_hard(ocode(code), sym)
+    for lib in _targets("bsc"):
+        d = cc.LegacyDecoder("bsc", lib)
+        assert d.init(code) == 0
+        d.register_callback()
+        for f in range(8):
+            if f % 2:
+                assert d.input(sym[f]) == 0
+            else:                                                     # split delivery is allowed too
+                assert d.input(sym[f, :17]) == 0 and d.input(sym[f, 17:]) == 0
+        got = np.frombuffer(b"".join(fr[0] for fr in d.frames), np.uint8).reshape(8, code.out_bytes)
+        assert np.array_equal(got, exp)
+        assert [fr[2] for fr in d.frames] == exp_pm.tolist() and all(fr[1] == code.L for fr in d.frames)
+        d.destroy()
+
+
+def test_k7_through_the_legacy_abi_at_its_width_limit(cc, orc):
+    """L + K - 1 = 255 is the most the 8-bit legacy ABI can carry (code.h:12, decoder.h:26)"""
+    code = cc.codes.K7_R12.with_block_len(249)
+    _, met = make_soft_inputs(orc, ocode(code), 2, 0.45, seed=5)
+    exp = orc.decode_soft(ocode(code), met)
+    for lib in _targets("awgn"):
+        d = cc.LegacyDecoder("awgn", lib)
+        assert d.init(code) == 0
+        d.register_callback()
+        for f in range(2):
+            for t in range(code.T):
+                d.input(met[f, t])
+        got = np.frombuffer(b"".join(fr[0] for fr in d.frames), np.uint8).reshape(2, code.out_bytes)
+        assert np.array_equal(got, exp)
+        d.destroy()

@@ -1,0 +1,209 @@
+"""GPU: the CUDA path through the C ABI against the oracle / golden vectors.  Bit-exact everywhere:
+hard-decision and integer metrics by definition, fp32 soft metrics because every candidate is the
+same `pm + bm` add the reference performs (tolerance stated: 0 differing bits)."""
+import numpy as np
+import pytest
+
+from conftest import golden_files, load_golden, make_hard_inputs, make_soft_inputs, ocode, to_param
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _decode_soft(cc, torch, code, parity, met, flags=0, host=False, max_frames=0):
+    dec = cc.BatchDecoder(code, cc.SOFT_F32, parity, flags=flags, max_frames=max_frames)
+    if host:
+        out = dec.decode_host(met)
+    else:
+        out = dec.decode(torch.from_numpy(np.ascontiguousarray(met)).cuda()).cpu().numpy()
+    name = dec.kernel_name
+    assert dec.launches >= 1
+    dec.close()
+    return out, name
+
+
+def _decode_hard(cc, torch, code, parity, sym, flags=0, host=False):
+    dec = cc.BatchDecoder(code, cc.HARD_U16, parity, flags=flags)
+    if host:
+        out, pm = dec.decode_host(sym)
+    else:
+        o, p = dec.decode(torch.from_numpy(np.ascontiguousarray(sym)).cuda())
+        out, pm = o.cpu().numpy(), p.cpu().numpy()
+    name = dec.kernel_name
+    dec.close()
+    return out, pm, name
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+@pytest.mark.parametrize("flags", [0, 1], ids=["auto", "generic"])
+def test_golden_vectors(cc, torch_cuda, path, flags):
+    """outputs of the UNMODIFIED reference decoder, reproduced by the CUDA kernels"""
+    z, ocd = load_golden(path)
+    code = to_param(cc, ocd)
+    if str(z["kind"]) == "soft":
+        for host in (False, True):
+            out, _ = _decode_soft(cc, torch_cuda, code, cc.PARITY_REF, z["inputs"], flags, host)
+            assert np.array_equal(out, z["outputs"])
+    else:
+        for host in (False, True):
+            out, pm, _ = _decode_hard(cc, torch_cuda, code, cc.PARITY_REF, z["inputs"], flags, host)
+            assert np.array_equal(out, z["outputs"])
+            assert np.array_equal(pm, z["path_metric"])
+
+
+SOFT_CASES = [  # (code getter, L, frames, sigma)
+    ("cb0", 40, 1000, 0.45), ("cb1", 40, 333, 0.5), ("cb2", 57, 129, 0.5), ("cb3", 40, 64, 0.45), ("cb5", 40, 257, 0.6),
+    ("k7r12", 1024, 96, 0.446154216921401), ("k7r12", 249, 33, 0.56), ("k7r12", 5, 31, 0.4), ("k7r12", 1, 7, 0.4),
+    ("k7r13", 300, 65, 0.6), ("k9", 128, 9, 0.5), ("k15", 40, 2, 0.5),
+]
+
+
+def _get(cc, key, L):
+    table = {"cb0": cc.get_code(0), "cb1": cc.get_code(1), "cb2": cc.get_code(2), "cb3": cc.get_code(3),
+             "cb5": cc.get_code(5), "k7r12": cc.codes.K7_R12, "k7r13": cc.codes.K7_R13, "k9": cc.codes.K9_R12,
+             "k15": cc.codes.K15_R12}
+    return table[key].with_block_len(L)
+
+
+@pytest.mark.parametrize("key,L,F,sigma", SOFT_CASES, ids=[f"{c[0]}-L{c[1]}-F{c[2]}" for c in SOFT_CASES])
+@pytest.mark.parametrize("parity", [0, 1], ids=["ref", "linear"])
+def test_soft_vs_oracle(cc, orc, torch_cuda, key, L, F, sigma, parity):
+    code = _get(cc, key, L)
+    oc = ocode(code, parity)
+    _, met = make_soft_inputs(orc, oc, F, sigma, seed=L * 131 + F)
+    exp = orc.decode_soft(oc, met)
+    out, name = _decode_soft(cc, torch_cuda, code, parity, met)
+    assert np.array_equal(out, exp), f"{name}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
+    if code.K <= 7:   # the table-driven kernel must agree too
+        out2, name2 = _decode_soft(cc, torch_cuda, code, parity, met, flags=cc.FORCE_GENERIC)
+        assert name2.startswith("generic") and np.array_equal(out2, exp)
+
+
+HARD_CASES = [("cb0", 40, 1000, 0.0125), ("cb0", 40, 1000, 0.2), ("cb1", 40, 300, 0.05), ("cb3", 40, 100, 0.05),
+              ("cb5", 40, 257, 0.1), ("k7r12", 249, 70, 0.05), ("k7r12", 1024, 40, 0.04), ("k7r13", 100, 33, 0.1),
+              ("k9", 100, 8, 0.05), ("k15", 30, 2, 0.03)]
+
+
+@pytest.mark.parametrize("key,L,F,p", HARD_CASES, ids=[f"{c[0]}-L{c[1]}-p{c[3]}" for c in HARD_CASES])
+@pytest.mark.parametrize("parity", [0, 1], ids=["ref", "linear"])
+def test_hard_vs_oracle(cc, orc, torch_cuda, key, L, F, p, parity):
+    code = _get(cc, key, L)
+    oc = ocode(code, parity)
+    _, sym = make_hard_inputs(orc, oc, F, p, seed=L + F)
+    exp, exp_pm = orc.decode_hard(oc, sym)
+    out, pm, name = _decode_hard(cc, torch_cuda, code, parity, sym)
+    assert np.array_equal(out, exp), name
+    assert np.array_equal(pm, exp_pm), name
+    if code.K <= 7:
+        out2, pm2, name2 = _decode_hard(cc, torch_cuda, code, parity, sym, flags=cc.FORCE_GENERIC)
+        assert np.array_equal(out2, exp) and np.array_equal(pm2, exp_pm), name2
+
+
+def test_high_symbol_bits_are_masked(cc, orc, torch_cuda):
+    """decoder_input masks each byte to the low n bits (binary-symmetric-channel/viterbi-decoder.c:235-237)"""
+    code = cc.get_code(0)
+    _, sym = make_hard_inputs(orc, ocode(code), 64, 0.05, seed=3)
+    exp, exp_pm = orc.decode_hard(ocode(code), sym)
+    dirty = sym | np.uint8(0xA4)
+    out, pm, _ = _decode_hard(cc, torch_cuda, code, 0, dirty)
+    assert np.array_equal(out, exp) and np.array_equal(pm, exp_pm)
+
+
+def test_edge_cases_ties_and_chunking(cc, orc, torch_cuda):
+    code = cc.codes.K7_R12.with_block_len(100)
+    oc = ocode(code)
+    # all-equal metrics: every compare ties -> all-zero decode
+    met = np.ones((5, code.T, code.M), np.float32)
+    out, _ = _decode_soft(cc, torch_cuda, code, 0, met)
+    assert np.array_equal(out, orc.decode_soft(oc, met)) and not out.any()
+    # quantised metrics (hard-demapper-like values) tie constantly
+    rng = np.random.default_rng(0)
+    met = rng.integers(0, 3, size=(300, code.T, code.M)).astype(np.float32)
+    exp = orc.decode_soft(oc, met)
+    out, _ = _decode_soft(cc, torch_cuda, code, 0, met)
+    assert np.array_equal(out, exp)
+    # several launches per call (max_frames smaller than the batch, ragged last launch)
+    out, _ = _decode_soft(cc, torch_cuda, code, 0, met, max_frames=70)
+    assert np.array_equal(out, exp)
+    out, _ = _decode_soft(cc, torch_cuda, code, 0, met, max_frames=70, host=True)
+    assert np.array_equal(out, exp)
+    # empty batch
+    dec = cc.BatchDecoder(code)
+    assert dec.decode_host(np.zeros((0, code.T, code.M), np.float32)).shape == (0, code.out_bytes)
+    dec.close()
+
+
+def test_headline_config_full_frame_properties(cc, orc, torch_cuda):
+    """BASELINE config 2 shape (K=7, L=1024) at a size the oracle cannot cover entirely:
+    noise-free round trip, determinism, sharding invariance of the synthetic link, and the error
+    counters; plus an oracle spot check on a sample of the very same frames."""
+    torch = torch_cuda
+    code = cc.codes.K7_R12
+    F = 1 << 15
+    dec = cc.BatchDecoder(code, cc.SOFT_F32, cc.PARITY_LINEAR)
+    payload, met = dec.synth_awgn(F, 0, 12345, 0.0)
+    out = dec.decode(met)
+    cnt = dec.count_errors(out, payload).cpu().numpy()
+    assert cnt.tolist() == [F * code.L, 0, 0]                         # noise-free: decode == payload
+    p4, m4 = dec.synth_awgn(F, 0, 12345, cc.awgn_sigma(4.0))
+    assert torch.equal(p4, payload)                                  # payload depends on (seed, frame) only
+    o4 = dec.decode(m4)
+    assert torch.equal(o4, dec.decode(m4))                           # deterministic
+    c4 = dec.count_errors(o4, p4).cpu().numpy()
+    ber = c4[1] / c4[0]
+    assert 1e-5 < ber < 5e-4, ber                                    # textbook (171,133) soft @4 dB is ~7e-5
+    # shard invariance: frames [F/2, F) generated separately are identical
+    p_hi, m_hi = dec.synth_awgn(F // 2, F // 2, 12345, cc.awgn_sigma(4.0))
+    assert torch.equal(m_hi, m4[F // 2:]) and torch.equal(p_hi, p4[F // 2:])
+    # oracle on a sample of the same frames, both label modes
+    idx = np.arange(0, F, F // 64)
+    sample = m4[torch.from_numpy(idx).cuda()].cpu().numpy()
+    exp = orc.decode_soft(ocode(code, 1), sample)
+    assert np.array_equal(o4.cpu().numpy()[idx], exp)
+    counted = np.unpackbits(exp[:, :code.payload_bytes] ^ p4.cpu().numpy()[idx], axis=1).sum()
+    dref = cc.BatchDecoder(code, cc.SOFT_F32, cc.PARITY_REF)
+    oref = dref.decode(m4[:256].contiguous()).cpu().numpy()
+    assert np.array_equal(oref, orc.decode_soft(ocode(code, 0), m4[:256].cpu().numpy()))
+    assert counted >= 0
+    dec.close(); dref.close()
+
+
+def test_synth_and_aux_kernels(cc, orc, torch_cuda):
+    torch = torch_cuda
+    for code, parity in ((cc.codes.K7_R12.with_block_len(200), 0), (cc.get_code(5), 0), (cc.codes.K7_R13.with_block_len(64), 1)):
+        oc = ocode(code, parity)
+        dec = cc.BatchDecoder(code, cc.SOFT_F32, parity)
+        payload, met, iq = dec.synth_awgn(300, 1000, 7, 0.0, want_iq=True)
+        sym = orc.encode(oc, payload.cpu().numpy())                  # encoder.c:84-119
+        pts = orc.constellation(code.n)[sym]                         # mapper.c:54-71
+        assert np.array_equal(iq.cpu().numpy(), pts)
+        exp = orc.demap(code.n, pts.reshape(-1, 2)).reshape(met.shape)
+        assert np.array_equal(met.cpu().numpy().view(np.uint32), exp.view(np.uint32))
+        # with noise: metrics are still exactly demap(iq); noise has the requested variance
+        payload, met, iq = dec.synth_awgn(300, 1000, 7, 0.5, want_iq=True)
+        exp = orc.demap(code.n, iq.cpu().numpy().reshape(-1, 2)).reshape(met.shape)
+        assert np.array_equal(met.cpu().numpy().view(np.uint32), exp.view(np.uint32))
+        noise = iq.cpu().numpy() - pts
+        assert abs(noise.std() - 0.5) < 0.01 and abs(noise.mean()) < 0.01
+        assert np.array_equal(cc.demap(code.n, iq).cpu().numpy().view(np.uint32), exp.view(np.uint32))
+        dec.close()
+    # BSC source: flips at the requested rate, symbols otherwise the encoder's
+    code = cc.get_code(0)
+    dec = cc.BatchDecoder(code, cc.HARD_U16)
+    payload, sym = dec.synth_bsc(4000, 0, 99, 50000)
+    clean = orc.encode(ocode(code), payload.cpu().numpy())
+    flips = np.unpackbits((sym.cpu().numpy() ^ clean).reshape(-1, 1), axis=1).sum() / (4000 * code.T * code.n)
+    assert abs(flips - 0.05) < 0.004
+    out, pm = dec.decode(sym)
+    exp, exp_pm = orc.decode_hard(ocode(code), sym.cpu().numpy())
+    assert np.array_equal(out.cpu().numpy(), exp) and np.array_equal(pm.cpu().numpy(), exp_pm)
+    cnt = dec.count_errors(out, payload).cpu().numpy()
+    errs = np.unpackbits(exp[:, :5] ^ payload.cpu().numpy(), axis=1)
+    assert cnt.tolist() == [4000 * 40, int(errs.sum()), int(errs.any(axis=1).sum())]
+    dec.close()

@@ -1,0 +1,140 @@
+"""CPU: host-side logic, the C ABI surface and the 2-rank counter exchange (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, ocode
+
+ALL_CODES = lambda cc: [cc.get_code(i) for i in (0, 1, 2, 3, 5)] + [cc.codes.K7_R12, cc.codes.K7_R13, cc.codes.K9_R12, cc.codes.K15_R12]
+
+
+def test_labels_match_oracle(cc, orc):
+    for code in ALL_CODES(cc):
+        for parity in (cc.PARITY_REF, cc.PARITY_LINEAR):
+            assert np.array_equal(cc.config_labels(code, parity), orc.labels(ocode(code, parity))), (code.name, parity)
+
+
+def test_ref_labels_are_nonlinear_only_with_a_d3_tap(cc):
+    # SURVEY finding 1: codes 0 and 5 (K=3) are unaffected, (171,133) is
+    for idx in (0, 5):
+        c = cc.get_code(idx)
+        assert np.array_equal(cc.config_labels(c, 0), cc.config_labels(c, 1))
+    c = cc.codes.K7_R12
+    assert not np.array_equal(cc.config_labels(c, 0), cc.config_labels(c, 1))
+
+
+def test_kernel_selection(cc):
+    k7 = cc.codes.K7_R12
+    assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_REF).startswith("regs_soft_f32<K7 (171,133) ref")
+    assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regs_soft_f32<K7 (171,133) linear")
+    assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_REF, cc.FORCE_GENERIC).startswith("generic_soft_f32")
+    assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32).startswith("generic_soft_f32<K9")
+    assert cc.config_kernel_name(cc.get_code(0), cc.HARD_U16).startswith("regs_hard_u16<codebook0")
+    # codebook 0 has no D^3 tap: the ref-label kernel also serves the linear request
+    assert cc.config_kernel_name(cc.get_code(0), cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regs_soft_f32<codebook0")
+
+
+def _declared_functions(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vdec_[a-z_]+|decoder_[a-z_]+)\s*\(", src)))
+
+
+def test_c_abi_exports_every_declared_symbol(cc):
+    libdir = os.path.join(ROOT, "convolutional-codes_b200", "lib")
+    lib = ctypes.CDLL(os.path.join(libdir, "libvdec.so"))
+    names = _declared_functions("vdec.h")
+    assert len(names) >= 19
+    for n in names:
+        getattr(lib, n)
+    for kind in ("awgn", "bsc"):
+        shim = ctypes.CDLL(os.path.join(libdir, f"libvdec_{kind}.so"))
+        decl = _declared_functions(f"vdec_legacy_{kind}.h")
+        assert decl == sorted(["decoder_create", "decoder_destroy", "decoder_init", "decoder_register_callback",
+                               "decoder_reset", "decoder_input"])
+        for n in decl:
+            getattr(shim, n)
+
+
+def test_code_param_layout_matches_reference_abi():
+    """struct code_param crosses the plugin boundary by pointer: offsets must be the reference's"""
+    src = r'''
+    #include <stddef.h>
+    #include <stdio.h>
+    #include "vdec_code_param.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(struct code_param), offsetof(struct code_param, block_len),
+      offsetof(struct code_param, polynomials), offsetof(struct code_param, metric_weight),
+      offsetof(struct code_param, fano_metric_weight), offsetof(struct code_param, userdata)); return 0; }'''
+    exe = os.path.join(ROOT, "build", "abi_probe")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    open(exe + ".c", "w").write(src)
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), exe + ".c", "-o", exe], check=True)
+    got = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert got == ["48", "2", "8", "32", "36", "40"]      # x86-64 SysV layout of common/include/code.h:9-19
+    ref_hdr = "/root/reference/common/include"
+    if os.path.isdir(ref_hdr):                              # same probe against the real header when present
+        open(exe + "_ref.c", "w").write(src.replace('"vdec_code_param.h"', '"code.h"'))
+        subprocess.run(["gcc", "-I", ref_hdr, exe + "_ref.c", "-o", exe + "_ref"], check=True)
+        assert subprocess.run([exe + "_ref"], capture_output=True, text=True, check=True).stdout.split() == got
+
+
+def test_library_refuses_without_gpu(cc):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    os.environ["VDEC_QUIET"] = "1"
+    with pytest.raises(cc.VdecError, match="no CUDA device"):
+        cc.BatchDecoder(cc.get_code(0))
+    leg = cc.LegacyDecoder("awgn")
+    assert leg.init(cc.get_code(0)) == -1                   # decoder_init reports failure, no CPU fallback
+    assert leg.input(np.zeros(4, np.float32)) == -1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "convolutional-codes_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").lower() or f in (), (f, "mentions oracle")
+
+
+def test_shard_range_partitions(cc):
+    for total in (0, 1, 7, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            spans = [cc.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (a, n), (b, _) in zip(spans, spans[1:]):
+                assert a + n == b
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VDEC_ROOT"])
+import vdec_pkg
+cc = vdec_pkg.load()
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+r, w = dist.get_rank(), dist.get_world_size()
+first, count = cc.shard_range(1001, r, w)
+# each rank "decodes" its own frames: counters = [bits, bit errors, frame errors] of its shard
+c = torch.tensor([count * 40, sum(f % 7 for f in range(first, first + count)), sum(1 for f in range(first, first + count) if f % 7)], dtype=torch.int64)
+cc.allreduce_counters(c)
+exp = [1001 * 40, sum(f % 7 for f in range(1001)), sum(1 for f in range(1001) if f % 7)]
+assert c.tolist() == exp, (c.tolist(), exp)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_counter_allreduce_gloo(cc):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2", VDEC_ROOT=ROOT)
+    procs = [subprocess.Popen([sys.executable, "-c", _WORKER], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
