@@ -147,22 +147,111 @@ __device__ __forceinline__ void argmin_phase(const typename MP::T (&r)[CD::S], t
     }
 }
 
+// ---- input feeders -----------------------------------------------------------------------------
+// Soft metrics arrive as [frame][step][M] floats: the 32 frames of a warp are 16 KB apart, so a
+// per-step load touches 32 different cache lines.  Each lane therefore streams ITS OWN frame row into
+// a private shared-memory ring with cp.async (LDGSTS, 16 B pieces, 128 B = one group at a time,
+// two groups ahead of the consumer), and the ACS loop reads its step with one conflict-free LDS.128.
+// No cross-lane sharing, hence no barrier: cp.async.wait_group is all the synchronisation needed.
+template <int M>
+struct SoftRing {
+    static constexpr int kStepBytes = M * 4;
+    static constexpr int kPieces = kStepBytes / 16;            // 16-byte pieces per step (M = 4, 8)
+    static constexpr int G = 128 / kStepBytes;                 // steps per prefetch group (one 128 B line)
+    static constexpr int NG = 3;                               // groups in the ring
+    static constexpr int kSlots = G * NG;
+    static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * kStepBytes;   // 12 KB
+    static_assert(M == 4 || M == 8, "soft ring feeder supports n = 2, 3");
+
+    uint32_t base;        // shared-window address of this lane's first piece
+    const float* src;     // this lane's frame row
+    uint32_t T;
+
+    __device__ __forceinline__ void prefetch_group(uint32_t g) const {
+        const uint32_t slot0 = (g % NG) * G;
+#pragma unroll
+        for (int s = 0; s < G; ++s) {
+            const uint32_t t = g * G + s;
+            if (t < T) {
+#pragma unroll
+                for (int c = 0; c < kPieces; ++c) {
+                    const uint32_t dst = base + (((slot0 + s) * kPieces + c) * 32) * 16;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)t * M + c * 4) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
+        base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * 16;
+        src = row; T = steps;
+        prefetch_group(0);
+        prefetch_group(1);
+    }
+    // branch metrics of step t (called with t = 0, 1, 2, ... in order)
+    __device__ __forceinline__ void get(uint32_t t, float (&bm)[M]) const {
+        if ((t % G) == 0) {
+            prefetch_group(t / G + 2);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");
+        }
+        const uint32_t slot = t % kSlots;
+#pragma unroll
+        for (int c = 0; c < kPieces; ++c) {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + ((slot * kPieces + c) * 32) * 16));
+            bm[4 * c] = v.x; bm[4 * c + 1] = v.y; bm[4 * c + 2] = v.z; bm[4 * c + 3] = v.w;
+        }
+    }
+    __device__ __forceinline__ void drain() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+};
+
+// Hard symbols are one byte per step; a warp's 32 frames are contiguous (32*T bytes), so plain
+// read-only loads stay in L1.
+template <int M>
+struct HardDirect {
+    static constexpr size_t kWarpBytes = 0;
+    const uint8_t* src;
+    __device__ __forceinline__ void init(void*, uint32_t, const uint8_t* row, uint32_t) { src = row; }
+    __device__ __forceinline__ void get(uint32_t t, uint32_t (&bm)[M]) const {
+        const uint32_t r = __ldg(src + t) & (M - 1);                                          // :235-237
+#pragma unroll
+        for (int e = 0; e < M; ++e) bm[e] = __popc(e ^ r);                                   // :69-72
+    }
+    __device__ __forceinline__ void drain() const {}
+};
+
+template <class MP, int M> struct FeederOf;
+template <int M> struct FeederOf<SoftF32, M> { using type = SoftRing<M>; };
+template <int M> struct FeederOf<HardU16, M> { using type = HardDirect<M>; };
+
+constexpr int kTraceChunk = 16;     // survivor words prefetched per traceback chunk
+
 template <class CD, class MP>
-__global__ void __launch_bounds__(kRegsThreads)
+__global__ void __launch_bounds__(kRegsThreads, 4)
 vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
                 uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words) {
     using MT = typename MP::T;
+    using Feeder = typename FeederOf<MP, CD::M>::type;
+    using SW = typename SurvWord<CD::NW>::type;
     constexpr int S = CD::S, B = CD::B, M = CD::M, NW = CD::NW;
-    extern __shared__ uint32_t s_stage[];            // [threads][stage_words] output staging
+    // dynamic shared memory: input rings [warps][kWarpBytes] during the forward pass, then reused as
+    // the output staging tile [threads][stage_words] (each warp only ever touches its own part)
+    extern __shared__ __align__(16) unsigned char s_raw[];
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t f = blockIdx.x * kRegsThreads + tid;
     const bool live = f < nframes;
     const uint32_t fr = live ? f : nframes - 1;      // dead lanes shadow the last frame, store nothing
     const size_t step_elems = MP::template step_elems<M>();
-    const typename MP::In* src = in + (size_t)fr * T * step_elems;
     // survivor scratch: [global warp][step][lane][NW]
     uint32_t* sv = surv + ((size_t)(f >> 5) * T * 32 + lane) * NW;
+    const size_t ring_bytes = Feeder::kWarpBytes, tile_bytes = (size_t)32 * stage_words * 4;
+    const size_t warp_smem = ring_bytes > tile_bytes ? ring_bytes : tile_bytes;
+    unsigned char* my_smem = s_raw + warp * warp_smem;
+
+    Feeder feed;
+    feed.init(my_smem, lane, in + (size_t)fr * T * step_elems, T);
 
     MT r[S];
     r[0] = 0;                                        // decoder_reset: state 0 starts at metric 0 (:215)
@@ -170,34 +259,28 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     for (int s = 1; s < S; ++s) r[s] = MP::init_rest();
 
     uint32_t dw[NW];
-    MT bm[M], bn[M];
-    MP::template load<M>(src, bm);
+    MT bm[M];
 
     // ---- forward pass: full periods of B steps, then the T % B remainder --------------------
     uint32_t t = 0;
     for (; t + B <= T; t += B) {
         static_for<0, B>([&](auto phc) {
             constexpr int PH = decltype(phc)::value;
-            const uint32_t tn = min(t + PH + 1, T - 1);
-            MP::template load<M>(src + (size_t)tn * step_elems, bn);      // one step of lookahead
+            feed.get(t + PH, bm);
             acs_step<CD, MP, PH>(r, bm, dw);
             if (live) surv_store<NW>(sv + (size_t)(t + PH) * 32 * NW, dw);
-#pragma unroll
-            for (int i = 0; i < M; ++i) bm[i] = bn[i];
         });
     }
     const uint32_t rem = T - t;                       // 0 .. B-1, warp-uniform
     static_for<0, B - 1>([&](auto phc) {
         constexpr int PH = decltype(phc)::value;
         if (PH < (int)rem) {
-            const uint32_t tn = min(t + PH + 1, T - 1);
-            MP::template load<M>(src + (size_t)tn * step_elems, bn);
+            feed.get(t + PH, bm);
             acs_step<CD, MP, PH>(r, bm, dw);
             if (live) surv_store<NW>(sv + (size_t)(t + PH) * 32 * NW, dw);
-#pragma unroll
-            for (int i = 0; i < M; ++i) bm[i] = bn[i];
         }
     });
+    feed.drain();
 
     // ---- final state: lowest-index argmin over logical states (:72-79) ----------------------
     MT best = MP::init_rest(); uint32_t cur = 0;
@@ -206,19 +289,41 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
         if (PH == (int)rem) argmin_phase<CD, MP, PH>(r, best, cur);
     });
     if (live && path_metric != nullptr) path_metric[f] = MP::to_path_metric(best);            // :94, :143
+    __syncwarp();                                     // ring reads are done before the tile is reused
 
     // ---- traceback (:81-89): decision of state `cur` at step tt, decoded bit = MSB of cur -----
-    uint32_t* stage = s_stage + (size_t)tid * stage_words;
-    uint32_t acc = 0;
-    if (live)
-    for (int tt = (int)T - 1; tt >= 0; --tt) {
-        uint32_t word;
-        if constexpr (NW == 1) word = sv[(size_t)tt * 32];
-        else word = sv[(size_t)tt * 64 + (cur >> 5)];
-        const uint32_t d = (word >> (cur & 31)) & 1u;
-        acc |= (cur >> (B - 1)) << (31 - (tt & 31));          // bit tt -> byte tt/8, bit 7-(tt%8)  (:88)
-        cur = ((cur << 1) & (S - 1)) | d;                      // predecessor (:86)
-        if ((tt & 31) == 0) { stage[tt >> 5] = __byte_perm(acc, 0, 0x0123); acc = 0; }
+    // The survivor words of a step do not depend on `cur`, so they are fetched a chunk ahead
+    // (coalesced: 32 lanes x NW words) and only the bit select is on the dependent chain.
+    uint32_t* stage = reinterpret_cast<uint32_t*>(my_smem) + (size_t)lane * stage_words;
+    if (live) {
+        const SW* svw = reinterpret_cast<const SW*>(sv);
+        SW wc[kTraceChunk], wn[kTraceChunk];
+        int base = ((int)T - 1) & ~(kTraceChunk - 1);
+#pragma unroll
+        for (int j = 0; j < kTraceChunk; ++j)
+            if (base + j < (int)T) wc[j] = __ldcg(svw + (size_t)(base + j) * 32);
+        uint32_t acc = 0;
+        for (; base >= 0; base -= kTraceChunk) {
+            if (base >= kTraceChunk) {
+#pragma unroll
+                for (int j = 0; j < kTraceChunk; ++j) wn[j] = __ldcg(svw + (size_t)(base - kTraceChunk + j) * 32);
+            }
+#pragma unroll
+            for (int j = kTraceChunk - 1; j >= 0; --j) {
+                const int tt = base + j;
+                if (tt < (int)T) {
+                    uint32_t word;
+                    if constexpr (NW == 1) word = wc[j];
+                    else word = (cur & 32) ? wc[j].y : wc[j].x;
+                    const uint32_t d = (word >> (cur & 31)) & 1u;
+                    acc |= (cur >> (B - 1)) << (31 - (tt & 31));      // bit tt -> byte tt/8, bit 7-(tt%8)  (:88)
+                    cur = ((cur << 1) & (S - 1)) | d;                  // predecessor (:86)
+                    if ((tt & 31) == 0) { stage[tt >> 5] = __byte_perm(acc, 0, 0x0123); acc = 0; }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kTraceChunk; ++j) wc[j] = wn[j];
+        }
     }
     __syncwarp();
 
@@ -227,7 +332,7 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     if (wbase < nframes) {
         const uint32_t rows = min(32u, nframes - wbase);
         const uint32_t total = rows * out_bytes;
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_stage + (size_t)(tid & ~31u) * stage_words);
+        const uint8_t* sb = reinterpret_cast<const uint8_t*>(my_smem);
         uint8_t* dst = out + (size_t)wbase * out_bytes;
         uint32_t row = 0, col = lane;
         while (col >= out_bytes) { col -= out_bytes; ++row; }
@@ -241,9 +346,13 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
 
 template <class CD, class MP>
 int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
+    using Feeder = typename FeederOf<MP, CD::M>::type;
     uint32_t stage_words = (g.out_bytes + 3) / 4;
     if ((stage_words & 1) == 0) ++stage_words;                 // odd stride: conflict-free column writes
-    const size_t smem = (size_t)kRegsThreads * stage_words * 4;
+    size_t warp_smem = (size_t)32 * stage_words * 4;
+    const size_t ring_bytes = Feeder::kWarpBytes;
+    if (ring_bytes > warp_smem) warp_smem = ring_bytes;
+    const size_t smem = (size_t)(kRegsThreads / 32) * warp_smem;
     auto kern = vit_regs_kernel<CD, MP>;
     if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (g.nframes + kRegsThreads - 1) / kRegsThreads;
