@@ -148,7 +148,7 @@ def run_reference(args) -> int:
         "e2e": {"value": gbit, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "acs_gstate_updates_per_s": gbit * 64 * 1030 / 1024,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -281,13 +281,22 @@ def run_gpu(args) -> int:
         "acs_gstate_updates_per_s": world * state_updates / 1e9,
         "bit_errors": {"bits": counters[0], "bit_errors": counters[1], "frame_errors": counters[2]},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line: dict) -> None:
+    """the ONE JSON line goes to the real stdout; everything else (NCCL banners, warnings) went to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+
+
 def main() -> int:
+    os.dup2(2, 1)                      # libraries that print to stdout (NCCL version banner) must not break the contract
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

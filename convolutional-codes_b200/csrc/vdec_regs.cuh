@@ -55,6 +55,7 @@ __device__ __forceinline__ void static_for(F&& f) {
 struct SoftF32 {
     using T = float;
     using In = float;
+    static constexpr bool kPacked = true;     // candidates formed with FADD2 on register pairs
     static constexpr uint32_t kMetric = VDEC_SOFT_F32;
     __device__ static __forceinline__ T init_rest() { return __int_as_float(0x7f800000); }   // +INF, :215-218
     // dst = min(ce, co), decision bit set iff co < ce  (strict: tie -> even predecessor)
@@ -86,6 +87,7 @@ struct SoftF32 {
 struct HardU16 {
     using T = uint32_t;      // uint16 semantics (clamp at 0xFF00) carried in 32-bit registers
     using In = uint8_t;
+    static constexpr bool kPacked = false;
     static constexpr uint32_t kMetric = VDEC_HARD_U16;
     __device__ static __forceinline__ T init_rest() { return 0xFF00u; }                      // :225-228
     __device__ static __forceinline__ void acs(T& dst, T pe, T po, T be, T bo, uint32_t& dw, uint32_t bit) {
@@ -126,6 +128,92 @@ __device__ __forceinline__ void acs_step(typename MP::T (&r)[CD::S], const typen
     }
 }
 
+// ---- packed-pair variant of the soft step (sm_100a add.rn.f32x2 = SASS FADD2) -----------------
+// Registers are held as 64-bit pairs (physical 2q, 2q+1).  One FADD2 forms two candidate metrics
+// in ONE issue slot; each lane of the packed add is an ordinary IEEE fp32 `pm + bm`, so results
+// stay bit-identical to the scalar recipe.  At phase 0 a pair is one butterfly's (even, odd)
+// members; at other phases it holds the same-parity members of two butterflies whose partners sit
+// in pair q ^ (1 << (pb-1)).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ float sel_lt(float ce, float co, uint32_t& dw, uint32_t bit) {
+    float dst;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.f32 p, %3, %2;\n\t"
+        "selp.f32 %0, %3, %2, p;\n\t"
+        "@p or.b32 %1, %1, %4;\n\t}"
+        : "=f"(dst), "+r"(dw) : "f"(ce), "f"(co), "r"(bit));
+    return dst;
+}
+
+// Which (bm[x], bm[y]) operand pairs does phase PH of this code need?  Bit x*M+y of the result.
+template <class CD, int PH>
+VDEC_HD constexpr uint64_t used_pairs_mask() {
+    constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M;
+    uint64_t m = 0;
+    for (int q = 0; q < S / 2; ++q) {
+        if (PB == 0) {
+            const uint32_t u = rotr_bits(2 * q, PH, B), v = u + 1;
+            for (uint32_t i = 0; i < 2; ++i) m |= 1ull << (CD::label(u, i) * M + CD::label(v, i));
+        } else {
+            if ((q >> (PB - 1)) & 1) continue;
+            const uint32_t u0 = rotr_bits(2 * q, PH, B), u1 = rotr_bits(2 * q + 1, PH, B);
+            for (uint32_t i = 0; i < 2; ++i) {
+                m |= 1ull << (CD::label(u0, i) * M + CD::label(u1, i));
+                m |= 1ull << (CD::label(u0 + 1, i) * M + CD::label(u1 + 1, i));
+            }
+        }
+    }
+    return m;
+}
+
+template <class CD, int PH>
+__device__ __forceinline__ void acs_step_f2(uint64_t (&rp)[CD::S / 2], const uint64_t (&bp)[CD::M * CD::M], uint32_t (&dw)[CD::NW]) {
+    constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M;
+#pragma unroll
+    for (int w = 0; w < CD::NW; ++w) dw[w] = 0;
+    if constexpr (PB == 0) {
+#pragma unroll
+        for (int q = 0; q < S / 2; ++q) {
+            const uint32_t u = rotr_bits(2 * q, PH, B), v = u + 1;
+            const uint32_t j0 = u >> 1, j1 = j0 + S / 2;
+            float e0, o0, e1, o1;
+            unpack2(fadd2(rp[q], bp[CD::label(u, 0) * M + CD::label(v, 0)]), e0, o0);
+            unpack2(fadd2(rp[q], bp[CD::label(u, 1) * M + CD::label(v, 1)]), e1, o1);
+            const float n0 = sel_lt(e0, o0, dw[j0 >> 5], 1u << (j0 & 31));
+            const float n1 = sel_lt(e1, o1, dw[j1 >> 5], 1u << (j1 & 31));
+            rp[q] = pack2(n0, n1);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < S / 2; ++q) {
+            if ((q >> (PB - 1)) & 1) continue;
+            const int q2 = q | (1 << (PB - 1));
+            const uint32_t u0 = rotr_bits(2 * q, PH, B), u1 = rotr_bits(2 * q + 1, PH, B);
+            const uint32_t v0 = u0 + 1, v1 = u1 + 1;
+            const uint32_t ja = u0 >> 1, jb = u1 >> 1;          // input-0 successors; +S/2 for input 1
+            float ea, eb, oa, ob, fa, fb, pa, pb_;
+            unpack2(fadd2(rp[q],  bp[CD::label(u0, 0) * M + CD::label(u1, 0)]), ea, eb);
+            unpack2(fadd2(rp[q2], bp[CD::label(v0, 0) * M + CD::label(v1, 0)]), oa, ob);
+            unpack2(fadd2(rp[q],  bp[CD::label(u0, 1) * M + CD::label(u1, 1)]), fa, fb);
+            unpack2(fadd2(rp[q2], bp[CD::label(v0, 1) * M + CD::label(v1, 1)]), pa, pb_);
+            const float na = sel_lt(ea, oa, dw[ja >> 5], 1u << (ja & 31));
+            const float nb = sel_lt(eb, ob, dw[jb >> 5], 1u << (jb & 31));
+            const float ma = sel_lt(fa, pa, dw[(ja + S / 2) >> 5], 1u << ((ja + S / 2) & 31));
+            const float mb = sel_lt(fb, pb_, dw[(jb + S / 2) >> 5], 1u << ((jb + S / 2) & 31));
+            rp[q] = pack2(na, nb);
+            rp[q2] = pack2(ma, mb);
+        }
+    }
+}
+
 template <int NW> struct SurvWord;
 template <> struct SurvWord<1> { using type = uint32_t; };
 template <> struct SurvWord<2> { using type = uint2; };
@@ -153,29 +241,32 @@ __device__ __forceinline__ void argmin_phase(const typename MP::T (&r)[CD::S], t
 // a private shared-memory ring with cp.async (LDGSTS, 16 B pieces, 128 B = one group at a time,
 // two groups ahead of the consumer), and the ACS loop reads its step with one conflict-free LDS.128.
 // No cross-lane sharing, hence no barrier: cp.async.wait_group is all the synchronisation needed.
-template <int M>
+template <int M, int B>
 struct SoftRing {
     static constexpr int kStepBytes = M * 4;
     static constexpr int kPieces = kStepBytes / 16;            // 16-byte pieces per step (M = 4, 8)
-    static constexpr int G = 128 / kStepBytes;                 // steps per prefetch group (one 128 B line)
+    static constexpr int G = B;                                // steps per prefetch group = one rotation period,
+                                                               // so the prefetch sits at phase 0 only (no per-step test)
     static constexpr int NG = 3;                               // groups in the ring
     static constexpr int kSlots = G * NG;
-    static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * kStepBytes;   // 12 KB
+    static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * kStepBytes;   // K=7, n=2: 9 KB
     static_assert(M == 4 || M == 8, "soft ring feeder supports n = 2, 3");
 
     uint32_t base;        // shared-window address of this lane's first piece
     const float* src;     // this lane's frame row
     uint32_t T;
+    uint32_t grp;         // group (= period) being consumed
+    uint32_t slot0;       // first ring slot of that group
 
     __device__ __forceinline__ void prefetch_group(uint32_t g) const {
-        const uint32_t slot0 = (g % NG) * G;
+        const uint32_t s0 = (g % NG) * G;
 #pragma unroll
         for (int s = 0; s < G; ++s) {
             const uint32_t t = g * G + s;
             if (t < T) {
 #pragma unroll
                 for (int c = 0; c < kPieces; ++c) {
-                    const uint32_t dst = base + (((slot0 + s) * kPieces + c) * 32) * 16;
+                    const uint32_t dst = base + (((s0 + s) * kPieces + c) * 32) * 16;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)t * M + c * 4) : "memory");
                 }
             }
@@ -184,35 +275,49 @@ struct SoftRing {
     }
     __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
         base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * 16;
-        src = row; T = steps;
+        src = row; T = steps; grp = 0; slot0 = 0;
         prefetch_group(0);
         prefetch_group(1);
     }
-    // branch metrics of step t (called with t = 0, 1, 2, ... in order)
-    __device__ __forceinline__ void get(uint32_t t, float (&bm)[M]) const {
-        if ((t % G) == 0) {
-            prefetch_group(t / G + 2);
-            asm volatile("cp.async.wait_group 2;" ::: "memory");
-        }
-        const uint32_t slot = t % kSlots;
-#pragma unroll
-        for (int c = 0; c < kPieces; ++c) {
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + ((slot * kPieces + c) * 32) * 16));
-            bm[4 * c] = v.x; bm[4 * c + 1] = v.y; bm[4 * c + 2] = v.z; bm[4 * c + 3] = v.w;
-        }
+    // start of a period: keep the ring two groups ahead, make the current group visible
+    __device__ __forceinline__ void begin_period() const {
+        prefetch_group(grp + 2);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+    }
+    __device__ __forceinline__ void end_period() {
+        ++grp;
+        slot0 = (slot0 == (NG - 1) * G) ? 0 : slot0 + G;
+    }
+    // packed mode: fetch every operand pair (bm[x], bm[y]) that MASK names straight into a 64-bit
+    // register pair with two scalar loads.  Volatile so that ptxas neither fuses them into a v4 load
+    // (which pins four consecutive registers and costs two MOVs per FADD2 operand) nor drops them.
+    template <uint64_t MASK, int PH>
+    __device__ __forceinline__ void get_pairs(uint64_t (&bp)[M * M]) const {
+        const uint32_t a = base + ((slot0 + PH) * kPieces * 32) * 16;
+        static_for<0, M * M>([&](auto ic) {
+            constexpr int I = decltype(ic)::value, x = I / M, y = I % M;
+            if constexpr ((MASK >> I) & 1ull) {
+                float lo, hi;
+                asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(lo) : "r"(a + (x / 4) * 512 + 4 * (x % 4)));
+                asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(hi) : "r"(a + (y / 4) * 512 + 4 * (y % 4)));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(bp[I]) : "f"(lo), "f"(hi));
+            } else {
+                bp[I] = 0;
+            }
+        });
     }
     __device__ __forceinline__ void drain() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };
 
 // Hard symbols are one byte per step; a warp's 32 frames are contiguous (32*T bytes), so plain
 // read-only loads stay in L1.
-template <int M>
+template <int M, int B>
 struct HardDirect {
     static constexpr size_t kWarpBytes = 0;
     const uint8_t* src;
     __device__ __forceinline__ void init(void*, uint32_t, const uint8_t* row, uint32_t) { src = row; }
+    __device__ __forceinline__ void begin_period() const {}
+    __device__ __forceinline__ void end_period() {}
     __device__ __forceinline__ void get(uint32_t t, uint32_t (&bm)[M]) const {
         const uint32_t r = __ldg(src + t) & (M - 1);                                          // :235-237
 #pragma unroll
@@ -221,9 +326,9 @@ struct HardDirect {
     __device__ __forceinline__ void drain() const {}
 };
 
-template <class MP, int M> struct FeederOf;
-template <int M> struct FeederOf<SoftF32, M> { using type = SoftRing<M>; };
-template <int M> struct FeederOf<HardU16, M> { using type = HardDirect<M>; };
+template <class MP, int M, int B> struct FeederOf;
+template <int M, int B> struct FeederOf<SoftF32, M, B> { using type = SoftRing<M, B>; };
+template <int M, int B> struct FeederOf<HardU16, M, B> { using type = HardDirect<M, B>; };
 
 constexpr int kTraceChunk = 16;     // survivor words prefetched per traceback chunk
 
@@ -232,7 +337,7 @@ __global__ void __launch_bounds__(kRegsThreads, 4)
 vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
                 uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words) {
     using MT = typename MP::T;
-    using Feeder = typename FeederOf<MP, CD::M>::type;
+    using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
     using SW = typename SurvWord<CD::NW>::type;
     constexpr int S = CD::S, B = CD::B, M = CD::M, NW = CD::NW;
     // dynamic shared memory: input rings [warps][kWarpBytes] during the forward pass, then reused as
@@ -257,6 +362,11 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     r[0] = 0;                                        // decoder_reset: state 0 starts at metric 0 (:215)
 #pragma unroll
     for (int s = 1; s < S; ++s) r[s] = MP::init_rest();
+    [[maybe_unused]] uint64_t rp[S / 2];             // packed mode: physical registers (2q, 2q+1) as one pair
+    if constexpr (MP::kPacked) {
+#pragma unroll
+        for (int q = 0; q < S / 2; ++q) rp[q] = pack2(r[2 * q], r[2 * q + 1]);
+    }
 
     uint32_t dw[NW];
     MT bm[M];
@@ -264,23 +374,42 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     // ---- forward pass: full periods of B steps, then the T % B remainder --------------------
     uint32_t t = 0;
     for (; t + B <= T; t += B) {
+        feed.begin_period();
         static_for<0, B>([&](auto phc) {
             constexpr int PH = decltype(phc)::value;
-            feed.get(t + PH, bm);
-            acs_step<CD, MP, PH>(r, bm, dw);
+            if constexpr (MP::kPacked) {
+                uint64_t bp[M * M];
+                feed.template get_pairs<used_pairs_mask<CD, PH>(), PH>(bp);
+                acs_step_f2<CD, PH>(rp, bp, dw);
+            } else {
+                feed.get(t + PH, bm);
+                acs_step<CD, MP, PH>(r, bm, dw);
+            }
             if (live) surv_store<NW>(sv + (size_t)(t + PH) * 32 * NW, dw);
         });
+        feed.end_period();
     }
     const uint32_t rem = T - t;                       // 0 .. B-1, warp-uniform
+    if (rem) feed.begin_period();
     static_for<0, B - 1>([&](auto phc) {
         constexpr int PH = decltype(phc)::value;
         if (PH < (int)rem) {
-            feed.get(t + PH, bm);
-            acs_step<CD, MP, PH>(r, bm, dw);
+            if constexpr (MP::kPacked) {
+                uint64_t bp[M * M];
+                feed.template get_pairs<used_pairs_mask<CD, PH>(), PH>(bp);
+                acs_step_f2<CD, PH>(rp, bp, dw);
+            } else {
+                feed.get(t + PH, bm);
+                acs_step<CD, MP, PH>(r, bm, dw);
+            }
             if (live) surv_store<NW>(sv + (size_t)(t + PH) * 32 * NW, dw);
         }
     });
     feed.drain();
+    if constexpr (MP::kPacked) {
+#pragma unroll
+        for (int q = 0; q < S / 2; ++q) unpack2(rp[q], r[2 * q], r[2 * q + 1]);
+    }
 
     // ---- final state: lowest-index argmin over logical states (:72-79) ----------------------
     MT best = MP::init_rest(); uint32_t cur = 0;
@@ -346,7 +475,7 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
 
 template <class CD, class MP>
 int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
-    using Feeder = typename FeederOf<MP, CD::M>::type;
+    using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
     uint32_t stage_words = (g.out_bytes + 3) / 4;
     if ((stage_words & 1) == 0) ++stage_words;                 // odd stride: conflict-free column writes
     size_t warp_smem = (size_t)32 * stage_words * 4;
