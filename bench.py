@@ -228,6 +228,23 @@ def run_gpu(args) -> int:
     e2e_gbit = world * Fe * code.L * e2e_steps / float(te.item()) / 1e9
     assert torch.equal(host_out.to(dev), out[:Fe]), "host-buffer path and device path disagree"
 
+    # ---- same, through the raw-I/Q entry (demapper fused behind the call: half the PCIe bytes per bit)
+    _, _, iq_dev = dec.synth_awgn(Fe, rank * F, SEED, sigma, want_iq=True)
+    host_iq = torch.empty((Fe, code.T, 2), dtype=torch.float32, pin_memory=True)
+    host_iq.copy_(iq_dev)
+    del iq_dev
+    for _ in range(2):
+        dec.decode_iq_host(host_iq, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dec.decode_iq_host(host_iq, out=host_out)
+    tq = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+    e2e_iq_gbit = world * Fe * code.L * e2e_steps / float(tq.item()) / 1e9
+    assert torch.equal(host_out.to(dev), out[:Fe]), "raw-I/Q path and metric path disagree"
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -276,6 +293,8 @@ def run_gpu(args) -> int:
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_gbit, "unit": UNIT, "h2d_bytes_per_step": Fe * dec.in_bytes, "d2h_bytes_per_step": Fe * dec.out_bytes,
                 "frames_per_step": Fe, "api": "vdec_decode_host (pinned host buffers, 2-stream pipeline)"},
+        "e2e_iq": {"value": e2e_iq_gbit, "unit": UNIT, "h2d_bytes_per_step": Fe * code.T * 8, "d2h_bytes_per_step": Fe * dec.out_bytes,
+                   "frames_per_step": Fe, "api": "vdec_decode_iq_host (raw I/Q in, demapper on the GPU; SURVEY 8f-2)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "acs_gstate_updates_per_s": world * state_updates / 1e9,

@@ -34,6 +34,11 @@ struct vdec_priv {
     vdec base;
     vdec_scratch sc;
     size_t stage_frames;      // capacity of the host pipeline buffers, in frames
+    float* met[3];            // demapped-metric staging for the raw-I/Q entry, per scratch slot
+    size_t met_frames[3];
+    float* iq_dev[2];         // device staging of host I/Q, per pipeline stage
+    uint8_t* iq_out[2];       // and of the decoded output
+    size_t iq_frames;
 };
 
 static vdec_priv* priv(vdec_t* h) { return reinterpret_cast<vdec_priv*>(h); }
@@ -47,6 +52,30 @@ static int ensure_scratch(vdec_priv* p, int slot, uint32_t frames) {
     if (p->sc.p[slot]) { VDEC_CUDA(cudaFree(p->sc.p[slot])); p->sc.p[slot] = nullptr; p->sc.bytes[slot] = 0; }
     VDEC_CUDA(cudaMalloc(&p->sc.p[slot], need));
     p->sc.bytes[slot] = need;
+    return 0;
+}
+
+// raw I/Q -> metrics (demap kernel) -> decode, in chunks that bound the metric staging buffer
+static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframes, uint8_t* out_dev, int32_t* pm_dev,
+                     cudaStream_t st);
+static int decode_iq_on(vdec_priv* p, int slot, const float* iq_dev, uint64_t nframes, uint8_t* out_dev, cudaStream_t st) {
+    vdec* h = &p->base;
+    if (h->cfg.metric != VDEC_SOFT_F32) { vd::set_error("raw-I/Q entry needs the soft metric"); return -1; }
+    const vd::LaunchGeom& g = h->geom;
+    size_t chunk = ((size_t)1 << 30) / ((size_t)g.T * g.M * 4);      // ~1 GiB of staged metrics
+    if (chunk < 1) chunk = 1;
+    if (chunk > nframes) chunk = nframes;
+    if (chunk > p->met_frames[slot]) {
+        if (p->met[slot]) { VDEC_CUDA(cudaFree(p->met[slot])); p->met[slot] = nullptr; p->met_frames[slot] = 0; }
+        VDEC_CUDA(cudaMalloc(&p->met[slot], chunk * g.T * g.M * sizeof(float)));
+        p->met_frames[slot] = chunk;
+    }
+    for (uint64_t done = 0; done < nframes; done += chunk) {
+        const uint64_t n = (nframes - done < chunk) ? (nframes - done) : chunk;
+        if (vd::demap_launch(g.n, iq_dev + done * g.T * 2, n * g.T, p->met[slot], st) != 0) return -1;
+        h->launches += 1;
+        if (decode_on(p, slot, p->met[slot], n, out_dev + done * g.out_bytes, nullptr, st) != 0) return -1;
+    }
     return 0;
 }
 
@@ -148,6 +177,8 @@ void vdec_destroy(vdec_t* h) {
     vdec_priv* p = priv(h);
     cudaSetDevice(h->device);
     for (int i = 0; i < 3; ++i) if (p->sc.p[i]) cudaFree(p->sc.p[i]);
+    for (int i = 0; i < 3; ++i) if (p->met[i]) cudaFree(p->met[i]);
+    for (int i = 0; i < 2; ++i) { if (p->iq_dev[i]) cudaFree(p->iq_dev[i]); if (p->iq_out[i]) cudaFree(p->iq_out[i]); }
     for (int i = 0; i < 2; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
         if (h->dev_out[i]) cudaFree(h->dev_out[i]);
@@ -250,6 +281,53 @@ int vdec_decode_host(vdec_t* h, const void* in_host, uint64_t nframes, uint8_t* 
     VDEC_CUDA(cudaStreamSynchronize(h->streams[0]));
     VDEC_CUDA(cudaStreamSynchronize(h->streams[1]));
     if (path_metric_host != nullptr && !want_pm) memset(path_metric_host, 0, nframes * sizeof(int32_t));
+    return 0;
+}
+
+int vdec_decode_iq_device(vdec_t* h, const float* iq_dev, uint64_t nframes, uint8_t* out_dev, void* cuda_stream) {
+    if (!h || (nframes && (!iq_dev || !out_dev))) { vd::set_error("vdec_decode_iq_device: null argument"); return -1; }
+    if (nframes == 0) return 0;
+    VDEC_CUDA(cudaSetDevice(h->device));
+    return decode_iq_on(priv(h), 0, iq_dev, nframes, out_dev, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vdec_decode_iq_host(vdec_t* h, const float* iq_host, uint64_t nframes, uint8_t* out_host) {
+    if (!h || (nframes && (!iq_host || !out_host))) { vd::set_error("vdec_decode_iq_host: null argument"); return -1; }
+    if (nframes == 0) return 0;
+    vdec_priv* p = priv(h);
+    VDEC_CUDA(cudaSetDevice(h->device));
+    const size_t ib = (size_t)h->geom.T * 2 * sizeof(float), ob = h->geom.out_bytes;
+    size_t chunk = ((size_t)64 << 20) / ib;
+    if (chunk < 1) chunk = 1;
+    if (chunk > h->max_frames) chunk = h->max_frames;
+    if (chunk > nframes) chunk = nframes;
+    if (chunk > p->iq_frames) {
+        for (int i = 0; i < 2; ++i) {
+            if (p->iq_dev[i]) { cudaFree(p->iq_dev[i]); p->iq_dev[i] = nullptr; }
+            if (p->iq_out[i]) { cudaFree(p->iq_out[i]); p->iq_out[i] = nullptr; }
+        }
+        p->iq_frames = 0;
+        for (int i = 0; i < 2; ++i) {
+            VDEC_CUDA(cudaMalloc(&p->iq_dev[i], chunk * ib));
+            VDEC_CUDA(cudaMalloc(&p->iq_out[i], chunk * ob));
+        }
+        p->iq_frames = chunk;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!h->streams[i]) VDEC_CUDA(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    uint64_t done = 0;
+    int stage = 0;
+    while (done < nframes) {
+        const uint64_t n = (nframes - done < chunk) ? (nframes - done) : chunk;
+        cudaStream_t st = h->streams[stage];
+        VDEC_CUDA(cudaMemcpyAsync(p->iq_dev[stage], iq_host + done * h->geom.T * 2, n * ib, cudaMemcpyHostToDevice, st));
+        if (decode_iq_on(p, 1 + stage, p->iq_dev[stage], n, p->iq_out[stage], st) != 0) return -1;
+        VDEC_CUDA(cudaMemcpyAsync(out_host + done * ob, p->iq_out[stage], n * ob, cudaMemcpyDeviceToHost, st));
+        done += n;
+        stage ^= 1;
+    }
+    VDEC_CUDA(cudaStreamSynchronize(h->streams[0]));
+    VDEC_CUDA(cudaStreamSynchronize(h->streams[1]));
     return 0;
 }
 

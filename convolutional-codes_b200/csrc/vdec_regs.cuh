@@ -143,14 +143,43 @@ __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
 __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
     uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
 }
-__device__ __forceinline__ float sel_lt(float ce, float co, uint32_t& dw, uint32_t bit) {
+// dst = min(ce, co); decision (co < ce, strict) is ADDED as the exact power of two `w` to a float
+// accumulator.  Pipe placement on sm_100a (measured, profiles/r01c): FSETP and FMNMX go to the ALU
+// pipe, the predicated FADD to either FMA pipe — unlike a predicated integer add, which shares the
+// FMA-heavy pipe with FADD2 and saturated it.  Up to 24 decisions per accumulator stay exact.
+__device__ __forceinline__ float sel_lt(float ce, float co, float& acc, float w) {
     float dst;
     asm("{\n\t.reg .pred p;\n\t"
         "setp.lt.f32 p, %3, %2;\n\t"
-        "selp.f32 %0, %3, %2, p;\n\t"
-        "@p or.b32 %1, %1, %4;\n\t}"
-        : "=f"(dst), "+r"(dw) : "f"(ce), "f"(co), "r"(bit));
+        "min.f32 %0, %2, %3;\n\t"
+        "@p add.f32 %1, %1, %4;\n\t}"
+        : "=f"(dst), "+f"(acc) : "f"(ce), "f"(co), "f"(w));
     return dst;
+}
+
+// decision j of a step lives in accumulator j / 24 with weight 2^(j % 24)
+constexpr int kAccBits = 24;
+VDEC_HD constexpr float acc_weight(uint32_t j) { return (float)(1u << (j % kAccBits)); }
+
+// float accumulators -> the survivor words (bit j of the step's S-bit decision vector = state j)
+template <int S>
+__device__ __forceinline__ void acc_to_words(const float (&da)[(S + kAccBits - 1) / kAccBits], uint32_t (&dw)[(S + 31) / 32]) {
+    constexpr int NA = (S + kAccBits - 1) / kAccBits, NW = (S + 31) / 32;
+    uint32_t u[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) u[a] = __float2uint_rz(da[a]);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            constexpr int dummy = 0; (void)dummy;
+            const int sh = kAccBits * a - 32 * w;
+            if (sh >= 0 && sh < 32) word |= u[a] << sh;
+            else if (sh < 0 && sh > -kAccBits) word |= u[a] >> (-sh);
+        }
+        dw[w] = word;
+    }
 }
 
 // Which (bm[x], bm[y]) operand pairs does phase PH of this code need?  Bit x*M+y of the result.
@@ -176,9 +205,10 @@ VDEC_HD constexpr uint64_t used_pairs_mask() {
 
 template <class CD, int PH>
 __device__ __forceinline__ void acs_step_f2(uint64_t (&rp)[CD::S / 2], const uint64_t (&bp)[CD::M * CD::M], uint32_t (&dw)[CD::NW]) {
-    constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M;
+    constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M, NA = (S + kAccBits - 1) / kAccBits;
+    float da[NA];
 #pragma unroll
-    for (int w = 0; w < CD::NW; ++w) dw[w] = 0;
+    for (int a = 0; a < NA; ++a) da[a] = 0.f;
     if constexpr (PB == 0) {
 #pragma unroll
         for (int q = 0; q < S / 2; ++q) {
@@ -187,8 +217,8 @@ __device__ __forceinline__ void acs_step_f2(uint64_t (&rp)[CD::S / 2], const uin
             float e0, o0, e1, o1;
             unpack2(fadd2(rp[q], bp[CD::label(u, 0) * M + CD::label(v, 0)]), e0, o0);
             unpack2(fadd2(rp[q], bp[CD::label(u, 1) * M + CD::label(v, 1)]), e1, o1);
-            const float n0 = sel_lt(e0, o0, dw[j0 >> 5], 1u << (j0 & 31));
-            const float n1 = sel_lt(e1, o1, dw[j1 >> 5], 1u << (j1 & 31));
+            const float n0 = sel_lt(e0, o0, da[j0 / kAccBits], acc_weight(j0));
+            const float n1 = sel_lt(e1, o1, da[j1 / kAccBits], acc_weight(j1));
             rp[q] = pack2(n0, n1);
         }
     } else {
@@ -204,14 +234,15 @@ __device__ __forceinline__ void acs_step_f2(uint64_t (&rp)[CD::S / 2], const uin
             unpack2(fadd2(rp[q2], bp[CD::label(v0, 0) * M + CD::label(v1, 0)]), oa, ob);
             unpack2(fadd2(rp[q],  bp[CD::label(u0, 1) * M + CD::label(u1, 1)]), fa, fb);
             unpack2(fadd2(rp[q2], bp[CD::label(v0, 1) * M + CD::label(v1, 1)]), pa, pb_);
-            const float na = sel_lt(ea, oa, dw[ja >> 5], 1u << (ja & 31));
-            const float nb = sel_lt(eb, ob, dw[jb >> 5], 1u << (jb & 31));
-            const float ma = sel_lt(fa, pa, dw[(ja + S / 2) >> 5], 1u << ((ja + S / 2) & 31));
-            const float mb = sel_lt(fb, pb_, dw[(jb + S / 2) >> 5], 1u << ((jb + S / 2) & 31));
+            const float na = sel_lt(ea, oa, da[ja / kAccBits], acc_weight(ja));
+            const float nb = sel_lt(eb, ob, da[jb / kAccBits], acc_weight(jb));
+            const float ma = sel_lt(fa, pa, da[(ja + S / 2) / kAccBits], acc_weight(ja + S / 2));
+            const float mb = sel_lt(fb, pb_, da[(jb + S / 2) / kAccBits], acc_weight(jb + S / 2));
             rp[q] = pack2(na, nb);
             rp[q2] = pack2(ma, mb);
         }
     }
+    acc_to_words<S>(da, dw);
 }
 
 template <int NW> struct SurvWord;

@@ -133,6 +133,37 @@ class BatchDecoder:
             raise VdecError(_lib.last_error())
         return (out, path_metric) if self.metric == HARD_U16 else out
 
+    # -- raw-I/Q entry: demapper + decoder in one call (common/demapper.c:61-85 + viterbi-decoder.c) --------
+    def decode_iq(self, iq, out=None, stream=None):
+        """iq: float32 [F,T,2] CUDA, the channel output per trellis step -> uint8 [F,(T+7)/8]."""
+        import torch
+        assert iq.is_cuda and iq.is_contiguous() and iq.dtype == torch.float32 and iq.shape[1:] == (self.T, 2)
+        F = iq.shape[0]
+        if out is None:
+            out = torch.empty((F, self.out_bytes), dtype=torch.uint8, device=iq.device)
+        rc = self.lib.vdec_decode_iq_device(self.h, C.c_void_p(iq.data_ptr()), F, C.c_void_p(out.data_ptr()),
+                                            self._stream_ptr(stream))
+        if rc != 0:
+            raise VdecError(_lib.last_error())
+        return out
+
+    def decode_iq_host(self, iq, out=None):
+        def ptr(a):
+            return a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
+        if isinstance(iq, np.ndarray):
+            iq = np.ascontiguousarray(iq, np.float32)
+            n = iq.size
+        else:
+            assert not iq.is_cuda and iq.is_contiguous()
+            n = iq.numel()
+        F = n // (self.T * 2)
+        assert F * self.T * 2 == n
+        if out is None:
+            out = np.empty((F, self.out_bytes), np.uint8)
+        if self.lib.vdec_decode_iq_host(self.h, C.c_void_p(ptr(iq)), F, C.c_void_p(ptr(out))) != 0:
+            raise VdecError(_lib.last_error())
+        return out
+
     def sync(self):
         if self.lib.vdec_sync(self.h) != 0:
             raise VdecError(_lib.last_error())

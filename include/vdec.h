@@ -95,6 +95,13 @@ int vdec_decode_device(vdec_t* h, const void* in_dev, uint64_t nframes, uint8_t*
  * This is the call a reference maintainer binds; the legacy shims use it. */
 int vdec_decode_host(vdec_t* h, const void* in_host, uint64_t nframes, uint8_t* out_host,
                      int32_t* path_metric_host);
+/* Raw-I/Q entry: replaces demapper_input + decoder_input together.  Input is what
+ * the channel delivers to the demapper (AWGN-channel/main.c:104): float32 [nframes][T][2] (I, Q) per
+ * trellis step; the branch metrics are formed on the GPU bit-exactly as common/demapper.c:66-70 does
+ * (constellation of common/constellations.c for symlen_out = 1..3) and decoded as above.  Halves the
+ * bytes that cross PCIe per decoded bit (8.2 instead of 16.2 at K=7, n=2).  Soft metric only. */
+int vdec_decode_iq_device(vdec_t* h, const float* iq_dev, uint64_t nframes, uint8_t* out_dev, void* cuda_stream);
+int vdec_decode_iq_host(vdec_t* h, const float* iq_host, uint64_t nframes, uint8_t* out_host);
 int vdec_sync(vdec_t* h);
 /* number of this library's kernels launched through `h` so far */
 uint64_t vdec_launch_count(const vdec_t* h);

@@ -207,3 +207,20 @@ def test_synth_and_aux_kernels(cc, orc, torch_cuda):
     errs = np.unpackbits(exp[:, :5] ^ payload.cpu().numpy(), axis=1)
     assert cnt.tolist() == [4000 * 40, int(errs.sum()), int(errs.any(axis=1).sum())]
     dec.close()
+
+
+def test_raw_iq_entry_matches_demapper_plus_decoder(cc, orc, torch_cuda):
+    """vdec_decode_iq_*: demapper (common/demapper.c:66-70) + decoder in one call, device and host buffers"""
+    for code, parity in ((cc.codes.K7_R12.with_block_len(300), 0), (cc.get_code(5), 0), (cc.codes.K9_R12.with_block_len(64), 1)):
+        oc = ocode(code, parity)
+        dec = cc.BatchDecoder(code, cc.SOFT_F32, parity)
+        F = 200 if code.K <= 7 else 6
+        _, _, iq = dec.synth_awgn(F, 0, 3, 0.5, want_iq=True)
+        met = orc.demap(code.n, iq.cpu().numpy().reshape(-1, 2)).reshape(F, code.T, code.M)
+        exp = orc.decode_soft(oc, met)
+        assert np.array_equal(dec.decode_iq(iq).cpu().numpy(), exp)
+        assert np.array_equal(dec.decode_iq_host(iq.cpu().numpy()), exp)
+        dec.close()
+    with pytest.raises(cc.VdecError):
+        d = cc.BatchDecoder(cc.get_code(0), cc.HARD_U16)
+        d.decode_iq_host(np.zeros((1, 42, 2), np.float32))

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Device-resident throughput of every BASELINE.json config shape (not the headline bench):
+decoded Gbit/s and ACS Gstate-updates/s per kernel family, CUDA-event timed, inputs in HBM.
+
+    python tools/bench_configs.py [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import vdec_pkg
+    cc = vdec_pkg.load()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    q = 8 if args.quick else 1
+    C = cc.codes
+    cases = [  # name, code, metric, parity, frames, flags
+        ("C1 hard K3 cb0 L40", cc.get_code(0), cc.HARD_U16, cc.PARITY_REF, (1 << 20) // q, 0),
+        ("C1' soft K3 cb0 L40", cc.get_code(0), cc.SOFT_F32, cc.PARITY_REF, (1 << 20) // q, 0),
+        ("cb3 soft K6 L40", cc.get_code(3), cc.SOFT_F32, cc.PARITY_REF, (1 << 20) // q, 0),
+        ("C2 soft K7 r1/2 L1024 ref", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, (1 << 19) // q, 0),
+        ("C2 soft K7 r1/2 L1024 linear", C.K7_R12, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 19) // q, 0),
+        ("C2h hard K7 r1/2 L1024", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, (1 << 19) // q, 0),
+        ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, (1 << 18) // q, 0),
+        ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 18) // q, 0),
+        ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),
+        ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 16384 // q, 0),
+        ("C4 soft K15 L1024", C.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 1024 // q, 0),
+    ]
+    for name, code, metric, parity, F, flags in cases:
+        dec = cc.BatchDecoder(code, metric, parity, flags=flags)
+        if metric == cc.SOFT_F32:
+            payload, x = dec.synth_awgn(F, 0, 1, cc.awgn_sigma(4.0))
+        else:
+            payload, x = dec.synth_bsc(F, 0, 1, 20000)
+        out = torch.empty((F, dec.out_bytes), dtype=torch.uint8, device="cuda")
+        pm = torch.empty((F,), dtype=torch.int32, device="cuda")
+        for _ in range(2):
+            dec.decode(x, out=out, path_metric=pm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            dec.decode(x, out=out, path_metric=pm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        cnt = dec.count_errors(out, payload).cpu().tolist()
+        print(json.dumps({"case": name, "kernel": dec.kernel_name, "frames": F, "ms": round(ms, 3),
+                          "gbit_s": round(F * code.L / ms / 1e6, 3),
+                          "gstate_upd_s": round(F * code.T * code.S / ms / 1e6, 1),
+                          "ber": cnt[1] / max(cnt[0], 1)}), flush=True)
+        dec.close()
+        del x, out
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
