@@ -96,7 +96,7 @@ static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframe
         if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
         else rc = vd::generic_launch(g, h->cfg.metric, h->bfly_labels_dev, in, out, pm, p->sc.p[slot], st);
         if (rc != 0) return -1;
-        h->launches += 1;
+        h->launches += h->regs ? 1 : 2;             // table-driven path = forward + traceback kernels
         done += n;
     }
     return 0;

@@ -1,18 +1,28 @@
-// vdec_generic.cu — table-driven Viterbi kernel for ANY code with K <= 15: ONE CTA PER FRAME.
+// vdec_generic.cu — table-driven Viterbi kernels for ANY code with K <= 15.
 //
 // Serves every trellis the specialised register kernels (vdec_regs.cuh) do not cover: K >= 8
 // (256 .. 16384 states, BASELINE config 4) and arbitrary polynomials.  Same arithmetic and tie
 // rules as the reference (AWGN-channel/viterbi-decoder.c:108-141, 71-90;
-// binary-symmetric-channel/viterbi-decoder.c:114-150, 75-96):
-//   * path metrics double-buffered in shared memory (2 x S x 4 B; K=15: 128 KB),
-//   * per-butterfly labels (4 bytes: l(2m,0), l(2m+1,0), l(2m,1), l(2m+1,1)) staged once per CTA
-//     in shared memory (K=15: 32 KB), generated on the host from the caller's polynomials,
-//   * thread m handles butterflies m, m+NT, ...: reads (pm[2m], pm[2m+1]) as one 8-byte access,
-//     writes pm'[m] and pm'[m+S/2]; decisions are gathered with __ballot_sync into 32-bit survivor
-//     words, one bit per state per step, and stored to an HBM scratch ([frame][step][S/32]),
-//   * final state: lowest-index argmin (block reduction on (metric, index)),
-//   * traceback by warp 0 lane 0 over the scratch (latency-bound; a few % of the forward pass
-//     for the large-K configurations this kernel is for).
+// binary-symmetric-channel/viterbi-decoder.c:114-150, 75-96).  Two launches per batch:
+//
+//  1. vit_generic_forward — ONE CTA PER FRAME.
+//     * path metrics double-buffered in shared memory (2 x S x 4 B; K=15: 128 KB);
+//     * per-butterfly labels (4 bytes: l(2m,0), l(2m+1,0), l(2m,1), l(2m+1,1)), generated on the
+//       host from the caller's polynomials: in registers when every thread owns one butterfly
+//       (S/2 <= block size), else staged once per CTA in shared memory (K=15: 32 KB);
+//     * the step's M branch metrics sit in a double-buffered shared array (written one step ahead),
+//       so `bm[label]` is one broadcast LDS instead of a select chain;
+//     * thread m handles butterflies m, m+NT, ...: reads (pm[2m], pm[2m+1]) as one 8-byte access,
+//       writes pm'[m] and pm'[m+S/2]; decisions are gathered with __ballot_sync into 32-bit
+//       survivor words, one bit per state per step, stored to HBM ([frame][step][S/32]);
+//     * final state: lowest-index argmin (block reduction on (metric, index)) -> final_state[frame].
+//
+//  2. vit_generic_traceback — ONE THREAD PER FRAME.
+//     The predecessor recurrence cur' = ((cur << 1) & (S-1)) | d shifts new decision bits in at the
+//     LSB, so the survivor WORD needed k steps later, (cur_k >> 5), is known from the current state
+//     for k <= 5.  Each thread therefore keeps five dependent-free loads in flight and only the bit
+//     select is on the serial chain; thousands of frames hide the remaining latency.  Inside a CTA the
+//     same walk costs ~1 us per step and dominated the first version of this file by 20x.
 #include <stdio.h>
 
 #include "vdec_internal.h"
@@ -20,8 +30,6 @@
 namespace vd {
 
 namespace {
-
-constexpr int kGenThreads = 256;
 
 struct SoftOps {
     using T = float;
@@ -34,75 +42,94 @@ struct HardOps {
     __device__ static T cand(T pm, T bm) { return min(pm + bm, 0xFF00u); }                     // :127-130
 };
 
-template <class OPS, bool HARD>
-__global__ void __launch_bounds__(kGenThreads)
-vit_generic_kernel(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, const void* __restrict__ in_v,
-                   uint8_t* __restrict__ out, int32_t* __restrict__ path_metric, uint32_t* __restrict__ surv) {
+// surv layout: [frame][step][nw] words; tail: final_state[nframes] words
+// ONE_EACH: S/2 <= blockDim, every thread owns (at most) one butterfly for the whole frame.
+template <class OPS, bool HARD, bool ONE_EACH>
+__global__ void __launch_bounds__(1024)
+vit_generic_forward(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, const void* __restrict__ in_v,
+                    int32_t* __restrict__ path_metric, uint32_t* __restrict__ surv, uint32_t* __restrict__ final_state) {
     using T = typename OPS::T;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* pm0 = reinterpret_cast<T*>(smem_raw);
     T* pm1 = pm0 + g.S;
-    uint32_t* lab = reinterpret_cast<uint32_t*>(pm1 + g.S);     // [S/2]
-    __shared__ T red_val[kGenThreads / 32];
-    __shared__ uint32_t red_idx[kGenThreads / 32];
-    __shared__ uint32_t s_cur;
+    uint32_t* lab = reinterpret_cast<uint32_t*>(pm1 + g.S);     // [S/2], only when a thread owns > 1 butterfly
+    __shared__ T bm_s[2][8];
+    __shared__ T red_val[32];
+    __shared__ uint32_t red_idx[32];
 
-    const uint32_t f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const uint32_t half = g.S >> 1;
-    uint32_t* sv = surv + (size_t)f * g.T * g.nw;
+    const uint32_t f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    const uint32_t half = g.S >> 1, nw = g.nw, T_ = g.T, M = g.M;
+    uint32_t* sv = surv + (size_t)f * T_ * nw;
 
-    for (uint32_t m = tid; m < half; m += kGenThreads) lab[m] = __ldg(bfly_labels + m);
-    for (uint32_t s = tid; s < g.S; s += kGenThreads) pm0[s] = (s == 0) ? T(0) : OPS::unreachable();   // :215-218
+    for (uint32_t s = tid; s < g.S; s += nt) pm0[s] = (s == 0) ? T(0) : OPS::unreachable();          // :215-218
+    if constexpr (!ONE_EACH) for (uint32_t m = tid; m < half; m += nt) lab[m] = __ldg(bfly_labels + m);
+
+    // threads 0..M-1 publish the branch metrics one step ahead of their use
+    const float* in_f = static_cast<const float*>(in_v) + (size_t)f * T_ * M + tid;
+    const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * T_;
+    const bool stager = tid < M;
+    auto stage_bm = [&](uint32_t t) {
+        if (stager && t < T_) {
+            if constexpr (HARD) bm_s[t & 1][tid] = __popc(tid ^ (__ldg(in_b + t) & (M - 1)));       // :69-72, :235-237
+            else bm_s[t & 1][tid] = __ldg(in_f + (size_t)t * M);
+        }
+    };
+    stage_bm(0);
     __syncthreads();
 
     T* cur = pm0; T* nxt = pm1;
-    const float* in_f = static_cast<const float*>(in_v) + (size_t)f * g.T * g.M;
-    const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * g.T;
-    const uint32_t iters = (half + kGenThreads - 1) / kGenThreads;
-
-    for (uint32_t t = 0; t < g.T; ++t) {
-        T bm[8];
-        if constexpr (HARD) {
-            const uint32_t r = __ldg(in_b + t) & (g.M - 1);                                      // :235-237
-#pragma unroll
-            for (uint32_t e = 0; e < 8; ++e) bm[e] = __popc(e ^ r);                              // :69-72
-        } else {
-            const float* p = in_f + (size_t)t * g.M;
-#pragma unroll
-            for (uint32_t e = 0; e < 8; ++e) bm[e] = (e < g.M) ? __ldg(p + e) : 0.f;
+    if constexpr (ONE_EACH) {
+        const bool active = tid < half;
+        const uint32_t m = active ? tid : 0;
+        const uint32_t lb = __ldg(bfly_labels + m);
+        const uint32_t l00 = lb & 0xFF, l01 = (lb >> 8) & 0xFF, l10 = (lb >> 16) & 0xFF, l11 = lb >> 24;
+        // survivor word slots this warp's lane 0 writes
+        const bool writer = active && lane == 0;
+        uint32_t* w0p = sv + (half >= 32 ? (m >> 5) : 0);
+        uint32_t* w1p = sv + ((m + half) >> 5);
+        for (uint32_t t = 0; t < T_; ++t) {
+            stage_bm(t + 1);
+            const T* bm = bm_s[t & 1];
+            const T pe = cur[2 * m], po = cur[2 * m + 1];
+            const T c00 = OPS::cand(pe, bm[l00]), c01 = OPS::cand(po, bm[l01]);
+            const T c10 = OPS::cand(pe, bm[l10]), c11 = OPS::cand(po, bm[l11]);
+            const bool d0 = active && (c01 < c00), d1 = active && (c11 < c10);                   // strict: tie -> even (:122)
+            if (active) { nxt[m] = d0 ? c01 : c00; nxt[m + half] = d1 ? c11 : c10; }
+            const uint32_t b0 = __ballot_sync(0xffffffffu, d0), b1 = __ballot_sync(0xffffffffu, d1);
+            if (writer) {
+                if (half >= 32) { *w0p = b0; *w1p = b1; }
+                else *w0p = b0 | (b1 << half);                  // S <= 32: one word per step
+            }
+            w0p += nw; w1p += nw;
+            __syncthreads();
+            T* tmp = cur; cur = nxt; nxt = tmp;
         }
-        for (uint32_t it = 0; it < iters; ++it) {
-            const uint32_t m = it * kGenThreads + tid;
-            bool d0 = false, d1 = false;
-            if (m < half) {
+    } else {
+        // half is a multiple of nt (both powers of two, half > nt)
+        for (uint32_t t = 0; t < T_; ++t) {
+            stage_bm(t + 1);
+            const T* bm = bm_s[t & 1];
+            uint32_t* row = sv + (size_t)t * nw;
+#pragma unroll 4
+            for (uint32_t m = tid; m < half; m += nt) {
                 const uint32_t lb = lab[m];
                 const T pe = cur[2 * m], po = cur[2 * m + 1];
-                // register array indexed dynamically -> select chain (M <= 8)
-                auto pick = [&](uint32_t e) -> T {
-                    T v = bm[0];
-#pragma unroll
-                    for (uint32_t k = 1; k < 8; ++k) v = (e == k) ? bm[k] : v;
-                    return v;
-                };
-                const T c00 = OPS::cand(pe, pick(lb & 0xFF)), c01 = OPS::cand(po, pick((lb >> 8) & 0xFF));
-                const T c10 = OPS::cand(pe, pick((lb >> 16) & 0xFF)), c11 = OPS::cand(po, pick(lb >> 24));
-                d0 = c01 < c00; d1 = c11 < c10;                                                   // strict: tie -> even (:122)
+                const T c00 = OPS::cand(pe, bm[lb & 0xFF]), c01 = OPS::cand(po, bm[(lb >> 8) & 0xFF]);
+                const T c10 = OPS::cand(pe, bm[(lb >> 16) & 0xFF]), c11 = OPS::cand(po, bm[lb >> 24]);
+                const bool d0 = c01 < c00, d1 = c11 < c10;
                 nxt[m] = d0 ? c01 : c00;
                 nxt[m + half] = d1 ? c11 : c10;
+                const uint32_t b0 = __ballot_sync(0xffffffffu, d0), b1 = __ballot_sync(0xffffffffu, d1);
+                if (lane == 0) { row[m >> 5] = b0; row[(m + half) >> 5] = b1; }
             }
-            const uint32_t w0 = __ballot_sync(0xffffffffu, d0), w1 = __ballot_sync(0xffffffffu, d1);
-            if (lane == 0 && (m < half)) {
-                if (half >= 32) { sv[(size_t)t * g.nw + (m >> 5)] = w0; sv[(size_t)t * g.nw + ((m + half) >> 5)] = w1; }
-                else sv[(size_t)t * g.nw] = w0 | (w1 << half);          // S <= 32: one word per step
-            }
+            __syncthreads();
+            T* tmp = cur; cur = nxt; nxt = tmp;
         }
-        __syncthreads();
-        T* tmp = cur; cur = nxt; nxt = tmp;
     }
 
     // final state: lowest-index argmin with strict '<' from the sentinel (:72-79)
     T best = OPS::unreachable(); uint32_t idx = 0xFFFFFFFFu;
-    for (uint32_t s = tid; s < g.S; s += kGenThreads) {
+    for (uint32_t s = tid; s < g.S; s += nt) {
         const T v = cur[s];
         if (v < best) { best = v; idx = s; }
     }
@@ -115,46 +142,95 @@ vit_generic_kernel(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, const
     if (lane == 0) { red_val[tid >> 5] = best; red_idx[tid >> 5] = idx; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < kGenThreads / 32; ++w)
+        for (uint32_t w = 1; w < (nt + 31) / 32; ++w)
             if (red_val[w] < best || (red_val[w] == best && red_idx[w] < idx)) { best = red_val[w]; idx = red_idx[w]; }
         if (idx == 0xFFFFFFFFu) idx = 0;                       // nothing below the sentinel -> state 0
-        s_cur = idx;
+        final_state[f] = idx;
         if (HARD && path_metric != nullptr) path_metric[f] = (int32_t)best;                       // :94,:143
     }
-    __syncthreads();
+}
 
-    // traceback (:81-89)
-    if (tid == 0) {
-        uint32_t c = s_cur;
-        uint8_t* o = out + (size_t)f * g.out_bytes;
-        uint32_t acc = 0;
-        for (int t = (int)g.T - 1; t >= 0; --t) {
-            const uint32_t word = __ldcg(sv + (size_t)t * g.nw + (c >> 5));
-            const uint32_t d = (word >> (c & 31)) & 1u;
-            acc |= (c >> (g.K - 2)) << (7 - (t & 7));
-            c = ((c << 1) & (g.S - 1)) | d;
-            if ((t & 7) == 0) { o[t >> 3] = (uint8_t)acc; acc = 0; }
+constexpr int kDepth = 5;      // survivor words in flight per thread (see file header)
+
+__global__ void __launch_bounds__(128)
+vit_generic_traceback(LaunchGeom g, const uint32_t* __restrict__ surv, const uint32_t* __restrict__ final_state,
+                      uint8_t* __restrict__ out) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= g.nframes) return;
+    const uint32_t* sv = surv + (size_t)f * g.T * g.nw;
+    uint8_t* o = out + (size_t)f * g.out_bytes;
+    uint32_t c = final_state[f];
+    const uint32_t smask = g.S - 1, msb = g.K - 2;
+    // pipe[k] = word needed at step (t - k), whose index is known from the state at step t
+    uint32_t pipe[kDepth];
+    int t = (int)g.T - 1;
+#pragma unroll
+    for (int k = 0; k < kDepth; ++k) {
+        const int tk = t - k;
+        pipe[k] = tk >= 0 ? __ldcg(sv + (size_t)tk * g.nw + (((c << k) & smask) >> 5)) : 0u;
+    }
+    uint32_t acc = 0;
+    while (t >= 0) {
+        // consume kDepth steps from the pipe, refilling each slot with the word kDepth steps further back
+#pragma unroll
+        for (int k = 0; k < kDepth; ++k) {
+            if (t >= 0) {
+                const uint32_t word = pipe[k];
+                const uint32_t d = (word >> (c & 31)) & 1u;
+                acc |= (c >> msb) << (7 - (t & 7));                                                 // :88
+                c = ((c << 1) & smask) | d;                                                          // :86
+                if ((t & 7) == 0) { o[t >> 3] = (uint8_t)acc; acc = 0; }
+                --t;
+                // state at step t (just computed) fixes the word index kDepth-1 steps further back
+                const int tn = t - (kDepth - 1);
+                pipe[k] = tn >= 0 ? __ldcg(sv + (size_t)tn * g.nw + (((c << (kDepth - 1)) & smask) >> 5)) : 0u;
+            }
         }
     }
 }
 
 }  // namespace
 
-size_t generic_surv_bytes(const LaunchGeom& g) { return (size_t)g.nframes * g.T * g.nw * sizeof(uint32_t); }
+size_t generic_surv_bytes(const LaunchGeom& g) {
+    return ((size_t)g.nframes * g.T * g.nw + g.nframes) * sizeof(uint32_t);       // survivors + final states
+}
 size_t generic_smem_bytes(const LaunchGeom& g) { return (size_t)g.S * 4 * 2 + (size_t)(g.S / 2) * 4; }
+
+// block size: one butterfly per thread up to 1024 threads; for larger trellises as many threads as
+// the shared-memory-limited CTA count per SM leaves room for (K=15: one CTA of 1024 threads per SM)
+static uint32_t generic_block_threads(const LaunchGeom& g) {
+    const uint32_t half = g.S / 2;
+    if (half <= 32) return 32;
+    if (half <= 1024) return half;
+    return 1024;
+}
+
+template <class OPS, bool HARD>
+static int generic_forward_launch(const LaunchGeom& g, const uint32_t* labels, const void* in, int32_t* path_metric,
+                                  uint32_t* surv, uint32_t* final_state, cudaStream_t st) {
+    const size_t smem = generic_smem_bytes(g);
+    const uint32_t nt = generic_block_threads(g);
+    if (g.S / 2 <= nt) {
+        auto k = vit_generic_forward<OPS, HARD, true>;
+        if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<g.nframes, nt, smem, st>>>(g, labels, in, path_metric, surv, final_state);
+    } else {
+        auto k = vit_generic_forward<OPS, HARD, false>;
+        if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<g.nframes, nt, smem, st>>>(g, labels, in, path_metric, surv, final_state);
+    }
+    VDEC_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
                    uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
-    const size_t smem = generic_smem_bytes(g);
-    if (metric == VDEC_HARD_U16) {
-        auto k = vit_generic_kernel<HardOps, true>;
-        if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<g.nframes, kGenThreads, smem, st>>>(g, bfly_labels_dev, in, out, path_metric, surv);
-    } else {
-        auto k = vit_generic_kernel<SoftOps, false>;
-        if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<g.nframes, kGenThreads, smem, st>>>(g, bfly_labels_dev, in, out, path_metric, surv);
-    }
+    uint32_t* final_state = surv + (size_t)g.nframes * g.T * g.nw;
+    const int rc = metric == VDEC_HARD_U16
+                       ? generic_forward_launch<HardOps, true>(g, bfly_labels_dev, in, path_metric, surv, final_state, st)
+                       : generic_forward_launch<SoftOps, false>(g, bfly_labels_dev, in, path_metric, surv, final_state, st);
+    if (rc != 0) return -1;
+    vit_generic_traceback<<<(g.nframes + 127) / 128, 128, 0, st>>>(g, surv, final_state, out);
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }

@@ -19,6 +19,7 @@ def main():
     cc = vdec_pkg.load()
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="substring filter on the case name")
     args = ap.parse_args()
     q = 8 if args.quick else 1
     C = cc.codes
@@ -36,6 +37,8 @@ def main():
         ("C4 soft K15 L1024", C.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 1024 // q, 0),
     ]
     for name, code, metric, parity, F, flags in cases:
+        if args.only and args.only not in name:
+            continue
         dec = cc.BatchDecoder(code, metric, parity, flags=flags)
         if metric == cc.SOFT_F32:
             payload, x = dec.synth_awgn(F, 0, 1, cc.awgn_sigma(4.0))
