@@ -6,8 +6,8 @@ the two legacy shim libraries; this package is the thin host-side mirror used by
 from . import codes
 from .codes import (CodeParam, FORCE_GENERIC, HARD_U16, PARITY_LINEAR, PARITY_REF, SOFT_F32, awgn_sigma, get_code)
 from .decoder import BatchDecoder, LegacyDecoder, VdecError, config_kernel_name, config_labels, demap
-from .link import allreduce_counters, shard_range, simulate_awgn_point
+from .link import allreduce_counters, ber_with_ci, shard_range, simulate_awgn_point, sweep_awgn, write_octave
 
 __all__ = ["codes", "CodeParam", "get_code", "awgn_sigma", "BatchDecoder", "LegacyDecoder", "VdecError",
            "config_labels", "config_kernel_name", "demap", "shard_range", "allreduce_counters",
-           "simulate_awgn_point", "PARITY_REF", "PARITY_LINEAR", "SOFT_F32", "HARD_U16", "FORCE_GENERIC"]
+           "simulate_awgn_point", "sweep_awgn", "write_octave", "ber_with_ci", "PARITY_REF", "PARITY_LINEAR", "SOFT_F32", "HARD_U16", "FORCE_GENERIC"]

@@ -26,8 +26,52 @@ def allreduce_counters(counters):
     return counters
 
 
+def ber_with_ci(bits: int, bit_errors: int, frame_errors: int):
+    """BER and a 95 % interval.  Decoder errors come in bursts, so the independent events are errored
+    FRAMES, not bits: relative half-width 1.96/sqrt(frame_errors) (0 errors: upper bound 3/bits)."""
+    if bits == 0:
+        return 0.0, 0.0, 1.0
+    ber = bit_errors / bits
+    if frame_errors == 0:
+        return 0.0, 0.0, 3.0 / bits
+    rel = 1.96 / (frame_errors ** 0.5)
+    return ber, max(0.0, ber * (1.0 - rel)), ber * (1.0 + rel)
+
+
+def sweep_awgn(dec, ebn0_db_list, frames_per_point, seed: int = 12345, rank: int = 0, world: int = 1,
+               chunk: int = 1 << 16, min_frame_errors: int = 0, max_frames: int = 0):
+    """The AWGN driver's Eb/N0 loop (AWGN-channel/main.c:193-234) on the GPU, frames sharded over ranks.
+    frames_per_point: int or list; with min_frame_errors > 0 a point keeps adding batches of that many
+    frames until the (all-rank) frame-error count is reached or max_frames is hit.
+    Returns a list of dicts {ebn0_db, bits, bit_errors, frame_errors, ber, ci95_lo, ci95_hi}."""
+    out = []
+    for i, db in enumerate(ebn0_db_list):
+        n = frames_per_point[i] if isinstance(frames_per_point, (list, tuple)) else frames_per_point
+        total = [0, 0, 0]
+        done = 0
+        while True:
+            c = simulate_awgn_point(dec, n, db, seed + 7919 * i, rank, world, chunk, first_frame=done)
+            c = c.cpu().tolist()
+            total = [a + b for a, b in zip(total, c)]
+            done += n
+            if min_frame_errors <= 0 or total[2] >= min_frame_errors or (max_frames and done >= max_frames):
+                break
+        ber, lo, hi = ber_with_ci(*total)
+        out.append({"ebn0_db": db, "bits": total[0], "bit_errors": total[1], "frame_errors": total[2],
+                    "ber": ber, "ci95_lo": lo, "ci95_hi": hi})
+    return out
+
+
+def write_octave(path: str, name: str, points) -> None:
+    """Append a result vector in the style of the reference's results/awgn_channel.m (:1, :14-28)."""
+    with open(path, "a") as f:
+        f.write("snr_%s = [%s];\n" % (name, " ".join("%g" % p["ebn0_db"] for p in points)))
+        f.write("bits_%s = [%s];\n" % (name, " ".join("%d" % p["bits"] for p in points)))
+        f.write("ber_%s = [%s];\n" % (name, " ".join("%.10f" % p["ber"] for p in points)))
+
+
 def simulate_awgn_point(dec, total_frames: int, ebn0_db: float, seed: int, rank: int = 0, world: int = 1,
-                        chunk: int = 1 << 16):
+                        chunk: int = 1 << 16, first_frame: int = 0):
     """One Eb/N0 point of the AWGN driver's loop (AWGN-channel/main.c:193-234), sharded over ranks.
     Returns a CUDA int64[3] tensor [bits, bit errors, frame errors] summed over all ranks."""
     import torch
@@ -37,7 +81,7 @@ def simulate_awgn_point(dec, total_frames: int, ebn0_db: float, seed: int, rank:
     done = 0
     while done < count:
         n = min(chunk, count - done)
-        payload, metrics = dec.synth_awgn(n, first + done, seed, awgn_sigma(ebn0_db))
+        payload, metrics = dec.synth_awgn(n, first_frame + first + done, seed, awgn_sigma(ebn0_db))
         out = dec.decode(metrics)
         dec.count_errors(out, payload, counters)
         done += n
