@@ -11,7 +11,8 @@ LIBDIR = os.path.join(HERE, "lib")
 class VdecConfig(C.Structure):
     _fields_ = [("symlen_out", C.c_uint32), ("constr_len", C.c_uint32), ("block_len", C.c_uint32),
                 ("metric", C.c_uint32), ("parity", C.c_uint32), ("flags", C.c_uint32),
-                ("device", C.c_int32), ("max_frames", C.c_uint32), ("polynomials", C.c_uint64 * 8)]
+                ("device", C.c_int32), ("max_frames", C.c_uint32), ("polynomials", C.c_uint64 * 8),
+                ("metric_max", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 EXPORTS = {

@@ -14,6 +14,7 @@ PARITY_REF = 0      # labels as the reference's 0x6996 expression evaluates (bit
 PARITY_LINEAR = 1   # true GF(2) parity (textbook code)
 SOFT_F32 = 0
 HARD_U16 = 1
+SOFT_U8 = 2        # quantised soft: small integer branch metrics, uint8 [F][T][M]
 FORCE_GENERIC = 1
 
 

@@ -21,7 +21,9 @@ void set_error(const char* fmt, ...) {
 }
 
 static size_t in_bytes_per_frame(const vdec* h) {
-    return h->cfg.metric == VDEC_HARD_U16 ? (size_t)h->geom.T : (size_t)h->geom.T * h->geom.M * sizeof(float);
+    if (h->cfg.metric == VDEC_HARD_U16) return (size_t)h->geom.T;
+    if (h->cfg.metric == VDEC_SOFT_U8) return (size_t)h->geom.T * h->geom.M;
+    return (size_t)h->geom.T * h->geom.M * sizeof(float);
 }
 
 }  // namespace vd
@@ -47,7 +49,7 @@ static int ensure_scratch(vdec_priv* p, int slot, uint32_t frames) {
     vdec* h = &p->base;
     vd::LaunchGeom g = h->geom;
     g.nframes = frames;
-    const size_t need = h->regs ? h->regs->surv_bytes(g) : vd::generic_surv_bytes(g);
+    const size_t need = h->regs2 ? vd::regs2_bytes(h->regs2, g) : h->regs ? h->regs->surv_bytes(g) : vd::generic_surv_bytes(g);
     if (need <= p->sc.bytes[slot]) return 0;
     if (p->sc.p[slot]) { VDEC_CUDA(cudaFree(p->sc.p[slot])); p->sc.p[slot] = nullptr; p->sc.bytes[slot] = 0; }
     VDEC_CUDA(cudaMalloc(&p->sc.p[slot], need));
@@ -93,13 +95,40 @@ static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframe
         uint8_t* out = out_dev + done * g.out_bytes;
         int32_t* pm = pm_dev ? pm_dev + done : nullptr;
         int rc;
-        if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
+        if (h->regs2) rc = vd::regs2_run(h->regs2, g, in, out, pm, p->sc.p[slot], st);
+        else if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
         else rc = vd::generic_launch(g, h->cfg.metric, h->bfly_labels_dev, in, out, pm, p->sc.p[slot], st);
         if (rc != 0) return -1;
-        h->launches += h->regs ? 1 : 2;             // table-driven path = forward + traceback kernels
+        h->launches += (h->regs && !h->regs2) ? 1 : 2;   // packed path = transpose + decode; table-driven = forward + traceback
         done += n;
     }
     return 0;
+}
+
+static const char* metric_tag(uint32_t metric) {
+    return metric == VDEC_HARD_U16 ? "hard_u16" : metric == VDEC_SOFT_U8 ? "soft_u8" : "soft_f32";
+}
+
+// kernel family for a config: packed 16-bit (integer metrics that provably stay below 2^15) >
+// specialised register kernel > table-driven
+static void select_kernels(const vdec_config* cfg, const uint8_t* labels, const vd::RegsEntry** regs,
+                           const vd::Regs2Entry** regs2) {
+    *regs = nullptr; *regs2 = nullptr;
+    if (cfg->flags & VDEC_FORCE_GENERIC) return;
+    const uint64_t T = (uint64_t)cfg->block_len + cfg->constr_len - 1;
+    // the register kernels stage a warp's output rows in shared memory: 16 B (32 B packed) per step and CTA
+    const bool fits1 = T * 16 <= 200 * 1024, fits2 = T * 32 <= 200 * 1024;
+    if (!fits1) return;
+    const bool small = T * (cfg->metric == VDEC_HARD_U16 ? cfg->symlen_out : (cfg->metric_max ? cfg->metric_max : 255)) < 0x8000u;
+    if (cfg->metric == VDEC_SOFT_U8) {
+        if (fits2 && small) *regs2 = vd::regs2_find(cfg->constr_len, cfg->symlen_out, 1, labels);
+        return;
+    }
+    // hard decisions: the 32-bit register kernel is currently the faster one (73 vs 60 Gbit/s at K=7,
+    // tools/bench_configs.py); the packed kernel serves labellings only it was instantiated for
+    *regs = vd::regs_find(cfg->constr_len, cfg->symlen_out, cfg->metric, labels);
+    if (!*regs && cfg->metric == VDEC_HARD_U16 && fits2 && small)
+        *regs2 = vd::regs2_find(cfg->constr_len, cfg->symlen_out, 0, labels);
 }
 
 extern "C" {
@@ -112,7 +141,7 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
     if (cfg->symlen_out < 1 || cfg->symlen_out > 3) { vd::set_error("symlen_out %u unsupported (1..3)", cfg->symlen_out); return -1; }
     if (cfg->constr_len < 2 || cfg->constr_len > 15) { vd::set_error("constr_len %u unsupported (2..15)", cfg->constr_len); return -1; }
     if (cfg->block_len < 1 || cfg->block_len > (1u << 24)) { vd::set_error("block_len %u unsupported", cfg->block_len); return -1; }
-    if (cfg->metric > VDEC_HARD_U16 || cfg->parity > VDEC_PARITY_LINEAR) { vd::set_error("bad metric/parity selector"); return -1; }
+    if (cfg->metric > VDEC_SOFT_U8 || cfg->parity > VDEC_PARITY_LINEAR) { vd::set_error("bad metric/parity selector"); return -1; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         vd::set_error("no CUDA device: this library has no CPU path"); return -1;
@@ -147,13 +176,13 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
     free(bl);
     if (e != cudaSuccess) { vd::set_error("label upload failed: %s", cudaGetErrorString(e)); vdec_destroy(h); return -1; }
 
-    h->regs = (cfg->flags & VDEC_FORCE_GENERIC) ? nullptr : vd::regs_find(g.K, g.n, cfg->metric, h->labels_host);
-    if (h->regs) {
-        snprintf(h->kernel_name, sizeof(h->kernel_name), "%s", h->regs->name);
+    select_kernels(cfg, h->labels_host, &h->regs, &h->regs2);
+    if (h->regs2 || h->regs) {
+        snprintf(h->kernel_name, sizeof(h->kernel_name), "%s", h->regs2 ? vd::regs2_name(h->regs2) : h->regs->name);
         h->max_frames = cfg->max_frames ? cfg->max_frames : (1u << 20);
     } else {
         snprintf(h->kernel_name, sizeof(h->kernel_name), "generic_%s<K%u n%u table-driven>",
-                 cfg->metric == VDEC_HARD_U16 ? "hard_u16" : "soft_f32", g.K, g.n);
+                 metric_tag(cfg->metric), g.K, g.n);
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
         if (vd::generic_smem_bytes(g) > (size_t)max_smem) {
@@ -214,11 +243,11 @@ const char* vdec_config_kernel_name(const struct vdec_config* cfg) {
     static thread_local char name[128];
     uint8_t labels[2 * 16384];
     if (vdec_config_labels(cfg, labels) != 0) return "";
-    const vd::RegsEntry* e = (cfg->flags & VDEC_FORCE_GENERIC) ? nullptr
-                             : vd::regs_find(cfg->constr_len, cfg->symlen_out, cfg->metric, labels);
-    if (e) snprintf(name, sizeof(name), "%s", e->name);
-    else snprintf(name, sizeof(name), "generic_%s<K%u n%u table-driven>", cfg->metric == VDEC_HARD_U16 ? "hard_u16" : "soft_f32",
-                  cfg->constr_len, cfg->symlen_out);
+    const vd::RegsEntry* e = nullptr; const vd::Regs2Entry* e2 = nullptr;
+    select_kernels(cfg, labels, &e, &e2);
+    if (e2) snprintf(name, sizeof(name), "%s", vd::regs2_name(e2));
+    else if (e) snprintf(name, sizeof(name), "%s", e->name);
+    else snprintf(name, sizeof(name), "generic_%s<K%u n%u table-driven>", metric_tag(cfg->metric), cfg->constr_len, cfg->symlen_out);
     return name;
 }
 

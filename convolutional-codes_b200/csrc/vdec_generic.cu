@@ -42,9 +42,16 @@ struct HardOps {
     __device__ static T cand(T pm, T bm) { return min(pm + bm, 0xFF00u); }                     // :127-130
 };
 
+struct QuantOps {             // VDEC_SOFT_U8: exact integer sums, no clamp (the float decoder has none)
+    using T = uint32_t;
+    __device__ static T unreachable() { return 0x3FFFFFFFu; }
+    __device__ static T cand(T pm, T bm) { return pm + bm; }
+};
+
 // surv layout: [frame][step][nw] words; tail: final_state[nframes] words
 // ONE_EACH: S/2 <= blockDim, every thread owns (at most) one butterfly for the whole frame.
-template <class OPS, bool HARD, bool ONE_EACH>
+// IN: 0 = float metrics, 1 = hard symbols (Hamming), 2 = uint8 metrics
+template <class OPS, int IN, bool ONE_EACH>
 __global__ void __launch_bounds__(1024)
 vit_generic_forward(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, const void* __restrict__ in_v,
                     int32_t* __restrict__ path_metric, uint32_t* __restrict__ surv, uint32_t* __restrict__ final_state) {
@@ -67,10 +74,12 @@ vit_generic_forward(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, cons
     // threads 0..M-1 publish the branch metrics one step ahead of their use
     const float* in_f = static_cast<const float*>(in_v) + (size_t)f * T_ * M + tid;
     const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * T_;
+    const uint8_t* in_q = static_cast<const uint8_t*>(in_v) + (size_t)f * T_ * M + tid;
     const bool stager = tid < M;
     auto stage_bm = [&](uint32_t t) {
         if (stager && t < T_) {
-            if constexpr (HARD) bm_s[t & 1][tid] = __popc(tid ^ (__ldg(in_b + t) & (M - 1)));       // :69-72, :235-237
+            if constexpr (IN == 1) bm_s[t & 1][tid] = __popc(tid ^ (__ldg(in_b + t) & (M - 1)));   // :69-72, :235-237
+            else if constexpr (IN == 2) bm_s[t & 1][tid] = __ldg(in_q + (size_t)t * M);
             else bm_s[t & 1][tid] = __ldg(in_f + (size_t)t * M);
         }
     };
@@ -146,7 +155,7 @@ vit_generic_forward(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, cons
             if (red_val[w] < best || (red_val[w] == best && red_idx[w] < idx)) { best = red_val[w]; idx = red_idx[w]; }
         if (idx == 0xFFFFFFFFu) idx = 0;                       // nothing below the sentinel -> state 0
         final_state[f] = idx;
-        if (HARD && path_metric != nullptr) path_metric[f] = (int32_t)best;                       // :94,:143
+        if (IN == 1 && path_metric != nullptr) path_metric[f] = (int32_t)best;                       // :94,:143
     }
 }
 
@@ -205,17 +214,17 @@ static uint32_t generic_block_threads(const LaunchGeom& g) {
     return 1024;
 }
 
-template <class OPS, bool HARD>
+template <class OPS, int IN>
 static int generic_forward_launch(const LaunchGeom& g, const uint32_t* labels, const void* in, int32_t* path_metric,
                                   uint32_t* surv, uint32_t* final_state, cudaStream_t st) {
     const size_t smem = generic_smem_bytes(g);
     const uint32_t nt = generic_block_threads(g);
     if (g.S / 2 <= nt) {
-        auto k = vit_generic_forward<OPS, HARD, true>;
+        auto k = vit_generic_forward<OPS, IN, true>;
         if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<g.nframes, nt, smem, st>>>(g, labels, in, path_metric, surv, final_state);
     } else {
-        auto k = vit_generic_forward<OPS, HARD, false>;
+        auto k = vit_generic_forward<OPS, IN, false>;
         if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<g.nframes, nt, smem, st>>>(g, labels, in, path_metric, surv, final_state);
     }
@@ -226,9 +235,9 @@ static int generic_forward_launch(const LaunchGeom& g, const uint32_t* labels, c
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
                    uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
     uint32_t* final_state = surv + (size_t)g.nframes * g.T * g.nw;
-    const int rc = metric == VDEC_HARD_U16
-                       ? generic_forward_launch<HardOps, true>(g, bfly_labels_dev, in, path_metric, surv, final_state, st)
-                       : generic_forward_launch<SoftOps, false>(g, bfly_labels_dev, in, path_metric, surv, final_state, st);
+    const int rc = metric == VDEC_HARD_U16  ? generic_forward_launch<HardOps, 1>(g, bfly_labels_dev, in, path_metric, surv, final_state, st)
+                   : metric == VDEC_SOFT_U8 ? generic_forward_launch<QuantOps, 2>(g, bfly_labels_dev, in, path_metric, surv, final_state, st)
+                                            : generic_forward_launch<SoftOps, 0>(g, bfly_labels_dev, in, path_metric, surv, final_state, st);
     if (rc != 0) return -1;
     vit_generic_traceback<<<(g.nframes + 127) / 128, 128, 0, st>>>(g, surv, final_state, out);
     VDEC_CUDA(cudaGetLastError());

@@ -43,6 +43,14 @@ const RegsEntry* regs_find(uint32_t K, uint32_t n, uint32_t metric, const uint8_
 int regs_count();
 const RegsEntry* regs_at(int i);
 
+// ---- packed 16-bit kernels, two frames per thread (vdec_regs2.cu) ---------------------------------
+struct Regs2Entry;
+const Regs2Entry* regs2_find(uint32_t K, uint32_t n, uint32_t mode, const uint8_t* labels);
+const char* regs2_name(const Regs2Entry* e);
+int regs2_run(const Regs2Entry* e, const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric,
+              uint32_t* scratch, cudaStream_t st);
+size_t regs2_bytes(const Regs2Entry* e, const LaunchGeom& g);
+
 // ---- generic table-driven kernels (vdec_generic.cu) ----------------------------------------
 // One CTA per frame, path metrics in shared memory, labels from a device table; any K <= 15.
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
@@ -71,6 +79,7 @@ struct vdec {
     uint8_t* labels_dev;             // [S][2]
     uint32_t* bfly_labels_dev;       // [S/2] packed l00 | l01<<8 | l10<<16 | l11<<24
     const vd::RegsEntry* regs;     // non-null => specialised kernel
+    const vd::Regs2Entry* regs2;   // non-null => packed 16-bit kernel (takes precedence)
     uint32_t* surv;                  // survivor scratch
     size_t surv_bytes;
     // host-buffer pipeline (vdec_decode_host)

@@ -16,7 +16,7 @@ from typing import Callable, Optional
 import numpy as np
 
 from . import _lib
-from .codes import CodeParam, HARD_U16, PARITY_REF, SOFT_F32
+from .codes import CodeParam, HARD_U16, PARITY_REF, SOFT_F32, SOFT_U8
 
 
 class VdecError(RuntimeError):
@@ -24,12 +24,13 @@ class VdecError(RuntimeError):
 
 
 def make_config(code: CodeParam, metric: int, parity: int, device: int = 0, flags: int = 0,
-                max_frames: int = 0) -> _lib.VdecConfig:
+                max_frames: int = 0, metric_max: int = 0) -> _lib.VdecConfig:
     cfg = _lib.VdecConfig()
     cfg.symlen_out, cfg.constr_len, cfg.block_len = code.symlen_out, code.constr_len, code.block_len
     cfg.metric, cfg.parity, cfg.flags, cfg.device, cfg.max_frames = metric, parity, flags, device, max_frames
     for i, p in enumerate(code.polynomials):
         cfg.polynomials[i] = p
+    cfg.metric_max = metric_max
     return cfg
 
 
@@ -43,9 +44,9 @@ def config_labels(code: CodeParam, parity: int = PARITY_REF) -> np.ndarray:
     return out
 
 
-def config_kernel_name(code: CodeParam, metric: int, parity: int = PARITY_REF, flags: int = 0) -> str:
+def config_kernel_name(code: CodeParam, metric: int, parity: int = PARITY_REF, flags: int = 0, metric_max: int = 0) -> str:
     lib = _lib.load()
-    cfg = make_config(code, metric, parity, flags=flags)
+    cfg = make_config(code, metric, parity, flags=flags, metric_max=metric_max)
     return lib.vdec_config_kernel_name(C.byref(cfg)).decode()
 
 
@@ -53,10 +54,10 @@ class BatchDecoder:
     """One decoder object per (code, metric, parity, device) — ``decoder_create`` + ``decoder_init``."""
 
     def __init__(self, code: CodeParam, metric: int = SOFT_F32, parity: int = PARITY_REF, device: int = 0,
-                 flags: int = 0, max_frames: int = 0):
+                 flags: int = 0, max_frames: int = 0, metric_max: int = 0):
         self.lib = _lib.load()
         self.code, self.metric, self.parity, self.device = code, metric, parity, device
-        cfg = make_config(code, metric, parity, device, flags, max_frames)
+        cfg = make_config(code, metric, parity, device, flags, max_frames, metric_max)
         h = C.c_void_p()
         if self.lib.vdec_create(C.byref(h), C.byref(cfg)) != 0:
             raise VdecError(_lib.last_error())
@@ -93,7 +94,7 @@ class BatchDecoder:
         """x: soft float32 [F,T,M] or hard uint8 [F,T], CUDA, contiguous -> uint8 [F,(T+7)/8]."""
         import torch
         assert x.is_cuda and x.is_contiguous()
-        assert x.dtype == (torch.uint8 if self.metric == HARD_U16 else torch.float32)
+        assert x.dtype == (torch.float32 if self.metric == SOFT_F32 else torch.uint8)
         F = x.shape[0]
         assert x.numel() * x.element_size() == F * self.in_bytes, "input shape does not match the code"
         if out is None:
@@ -114,7 +115,7 @@ class BatchDecoder:
         def ptr(a):
             return a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr()
         if isinstance(x, np.ndarray):
-            x = np.ascontiguousarray(x, np.uint8 if self.metric == HARD_U16 else np.float32)
+            x = np.ascontiguousarray(x, np.float32 if self.metric == SOFT_F32 else np.uint8)
             nbytes = x.nbytes
         else:
             assert not x.is_cuda and x.is_contiguous()

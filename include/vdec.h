@@ -14,6 +14,7 @@
  * Formats (identical to what the reference decoder consumes / produces):
  *   soft input   float32 [nframes][T][M]   M = 2^n demapper distances per trellis step
  *                                          (common/demapper.c:66-70 -> viterbi-decoder.c:224-236)
+ *   quantised    uint8   [nframes][T][M]   VDEC_SOFT_U8: integer branch metrics, same order as the soft input
  *   hard input   uint8   [nframes][T]      one n-bit symbol per step in the low bits
  *                                          (binary-symmetric-channel/viterbi-decoder.c:234-243)
  *   output       uint8   [nframes][(T+7)/8] decoded bits MSB-first, ALL T = L+K-1 bits
@@ -39,7 +40,11 @@ extern "C" {
 
 enum vdec_metric {
     VDEC_SOFT_F32 = 0,   /* AWGN-channel/viterbi-decoder.c: float path metrics, +INF = unreachable */
-    VDEC_HARD_U16 = 1    /* binary-symmetric-channel/viterbi-decoder.c: uint16 metrics clamped at 0xFF00 */
+    VDEC_HARD_U16 = 1,   /* binary-symmetric-channel/viterbi-decoder.c: uint16 metrics clamped at 0xFF00 */
+    VDEC_SOFT_U8  = 2    /* quantised soft mode: the soft decoder of AWGN-channel/viterbi-decoder.c
+                            fed with small non-negative INTEGER branch metrics (e.g. common/hard-demapper.c's
+                            {0,1,2}); input uint8 [nframes][T][M].  On such inputs the reference's float
+                            arithmetic is exact, so the integer kernels are bit-identical to it. */
 };
 
 enum vdec_parity {
@@ -65,6 +70,9 @@ struct vdec_config {
     int32_t  device;                   /* CUDA device ordinal */
     uint32_t max_frames;               /* frames per kernel launch; 0 = default */
     uint64_t polynomials[VDEC_MAX_POLY];
+    uint32_t metric_max;               /* VDEC_SOFT_U8: largest branch metric the caller will pass (0 = 255);
+                                          T * metric_max < 32768 selects the packed 16-bit kernels */
+    uint32_t reserved;
 };
 
 typedef struct vdec vdec_t;

@@ -34,7 +34,14 @@ def test_kernel_selection(cc):
     assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regs_soft_f32<K7 (171,133) linear")
     assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_REF, cc.FORCE_GENERIC).startswith("generic_soft_f32")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32).startswith("generic_soft_f32<K9")
+    # hard decisions: 32-bit register kernel; packed 16-bit kernel only for labellings the former lacks
     assert cc.config_kernel_name(cc.get_code(0), cc.HARD_U16).startswith("regs_hard_u16<codebook0")
+    assert cc.config_kernel_name(cc.codes.K7_R13, cc.HARD_U16).startswith("regs2_hard_u16x2<K7 (133,171,165) ref")
+    # frames too long for the shared-memory output tile go to the table-driven kernels
+    assert cc.config_kernel_name(cc.get_code(0).with_block_len(20000), cc.HARD_U16).startswith("generic_hard_u16")
+    # quantised soft mode: packed kernel if the caller bounds the metrics, table-driven otherwise
+    assert cc.config_kernel_name(k7, cc.SOFT_U8, metric_max=2).startswith("regs2_soft_u8x2<K7 (171,133) ref")
+    assert cc.config_kernel_name(k7, cc.SOFT_U8).startswith("generic_soft_u8")
     # codebook 0 has no D^3 tap: the ref-label kernel also serves the linear request
     assert cc.config_kernel_name(cc.get_code(0), cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regs_soft_f32<codebook0")
 

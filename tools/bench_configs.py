@@ -30,6 +30,7 @@ def main():
         ("C2 soft K7 r1/2 L1024 ref", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, (1 << 19) // q, 0),
         ("C2 soft K7 r1/2 L1024 linear", C.K7_R12, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 19) // q, 0),
         ("C2h hard K7 r1/2 L1024", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, (1 << 19) // q, 0),
+        ("f3 quant K7 r1/2 L1024 (u8 metrics <= 7)", C.K7_R12, cc.SOFT_U8, cc.PARITY_LINEAR, (1 << 19) // q, 0),
         ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, (1 << 18) // q, 0),
         ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 18) // q, 0),
         ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),
@@ -39,9 +40,13 @@ def main():
     for name, code, metric, parity, F, flags in cases:
         if args.only and args.only not in name:
             continue
-        dec = cc.BatchDecoder(code, metric, parity, flags=flags)
+        dec = cc.BatchDecoder(code, metric, parity, flags=flags, metric_max=7 if metric == cc.SOFT_U8 else 0)
         if metric == cc.SOFT_F32:
             payload, x = dec.synth_awgn(F, 0, 1, cc.awgn_sigma(4.0))
+        elif metric == cc.SOFT_U8:
+            payload, xf = dec.synth_awgn(F, 0, 1, cc.awgn_sigma(4.0))
+            x = torch.clamp(torch.round(xf * 2.0), max=7).to(torch.uint8)      # 3-bit quantised squared distances
+            del xf
         else:
             payload, x = dec.synth_bsc(F, 0, 1, 20000)
         out = torch.empty((F, dec.out_bytes), dtype=torch.uint8, device="cuda")
