@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("VDEC_LIB_DIR") or os.path.join(HERE, "lib")      # override: A/B tests of builds
 
 
 class VdecConfig(C.Structure):

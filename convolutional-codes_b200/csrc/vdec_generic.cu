@@ -24,6 +24,7 @@
 //     select is on the serial chain; thousands of frames hide the remaining latency.  Inside a CTA the
 //     same walk costs ~1 us per step and dominated the first version of this file by 20x.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "vdec_internal.h"
 
@@ -159,6 +160,100 @@ vit_generic_forward(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, cons
     }
 }
 
+// ---- forward kernel for S >= 64: BPT butterflies per thread, everything loop-invariant in registers ----
+// nt = (S/2)/BPT threads (a multiple of 32), thread `tid` owns butterflies m = i*nt + tid, i < BPT.  Labels
+// are unpacked once into registers, the two path-metric buffers and the two branch-metric buffers are
+// addressed by constants (the step loop is unrolled by two), and a warp's ballots of butterfly row i land
+// in survivor words (i*nt/32 + warp) and (S/64 + i*nt/32 + warp): natural bit order, bit s&31 of word s>>5.
+template <class OPS, int IN, int BPT>
+__global__ void __launch_bounds__(1024)
+vit_generic_forward_v2(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, const void* __restrict__ in_v,
+                       int32_t* __restrict__ path_metric, uint32_t* __restrict__ surv, uint32_t* __restrict__ final_state) {
+    using T = typename OPS::T;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* pm0 = reinterpret_cast<T*>(smem_raw);
+    T* pm1 = pm0 + g.S;
+    __shared__ T bm_s[2][8];
+    __shared__ T red_val[32];
+    __shared__ uint32_t red_idx[32];
+
+    const uint32_t f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x;
+    const uint32_t half = g.S >> 1, nw = g.nw, T_ = g.T, M = g.M;
+
+    uint32_t l00[BPT], l01[BPT], l10[BPT], l11[BPT];
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+        const uint32_t lb = __ldg(bfly_labels + i * nt + tid);
+        l00[i] = lb & 0xFF; l01[i] = (lb >> 8) & 0xFF; l10[i] = (lb >> 16) & 0xFF; l11[i] = lb >> 24;
+    }
+    for (uint32_t s = tid; s < g.S; s += nt) pm0[s] = (s == 0) ? T(0) : OPS::unreachable();          // :215-218
+
+    const bool stager = tid < M;
+    const float* in_f = static_cast<const float*>(in_v) + (size_t)f * T_ * M + tid;
+    const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * T_;
+    const uint8_t* in_q = static_cast<const uint8_t*>(in_v) + (size_t)f * T_ * M + tid;
+    auto stage_bm = [&](uint32_t t, T* dst) {                   // step t's metrics, one step ahead of their use
+        if (stager) {
+            const uint32_t tc = t < T_ ? t : T_ - 1;
+            if constexpr (IN == 1) dst[tid] = __popc(tid ^ (__ldg(in_b + tc) & (M - 1)));        // :69-72, :235-237
+            else if constexpr (IN == 2) dst[tid] = __ldg(in_q + (size_t)tc * M);
+            else dst[tid] = __ldg(in_f + (size_t)tc * M);
+        }
+    };
+    uint32_t* row = surv + (size_t)f * T_ * nw + warp;          // lane 0 of each warp writes its words
+    const uint32_t wstride = nt >> 5, hi_off = half >> 5;
+    auto step = [&](const T* __restrict__ cur, T* __restrict__ nxt, const T* __restrict__ bm) {
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const uint32_t m = i * nt + tid;
+            const T pe = cur[2 * m], po = cur[2 * m + 1];
+            const T c00 = OPS::cand(pe, bm[l00[i]]), c01 = OPS::cand(po, bm[l01[i]]);
+            const T c10 = OPS::cand(pe, bm[l10[i]]), c11 = OPS::cand(po, bm[l11[i]]);
+            const bool d0 = c01 < c00, d1 = c11 < c10;                                            // strict: tie -> even (:122)
+            nxt[m] = d0 ? c01 : c00;
+            nxt[m + half] = d1 ? c11 : c10;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, d0), b1 = __ballot_sync(0xffffffffu, d1);
+            if (lane == 0) { row[i * wstride] = b0; row[hi_off + i * wstride] = b1; }
+        }
+        row += nw;
+    };
+    stage_bm(0, bm_s[0]);
+    __syncthreads();
+    uint32_t t = 0;
+    for (; t + 2 <= T_; t += 2) {
+        stage_bm(t + 1, bm_s[1]);
+        step(pm0, pm1, bm_s[0]);
+        __syncthreads();
+        stage_bm(t + 2, bm_s[0]);
+        step(pm1, pm0, bm_s[1]);
+        __syncthreads();
+    }
+    const T* fin = pm0;
+    if (t < T_) { step(pm0, pm1, bm_s[0]); __syncthreads(); fin = pm1; }
+
+    // final state: lowest-index argmin with strict '<' from the sentinel (:72-79)
+    T best = OPS::unreachable(); uint32_t idx = 0xFFFFFFFFu;
+    for (uint32_t s = tid; s < g.S; s += nt) {
+        const T v = fin[s];
+        if (v < best) { best = v; idx = s; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const T ov = __shfl_down_sync(0xffffffffu, best, off);
+        const uint32_t oi = __shfl_down_sync(0xffffffffu, idx, off);
+        if (ov < best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if (lane == 0) { red_val[warp] = best; red_idx[warp] = idx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (uint32_t w = 1; w < (nt + 31) / 32; ++w)
+            if (red_val[w] < best || (red_val[w] == best && red_idx[w] < idx)) { best = red_val[w]; idx = red_idx[w]; }
+        if (idx == 0xFFFFFFFFu) idx = 0;
+        final_state[f] = idx;
+        if (IN == 1 && path_metric != nullptr) path_metric[f] = (int32_t)best;                    // :94,:143
+    }
+}
+
 constexpr int kDepth = 5;      // survivor words in flight per thread (see file header)
 
 __global__ void __launch_bounds__(128)
@@ -205,31 +300,40 @@ size_t generic_surv_bytes(const LaunchGeom& g) {
 }
 size_t generic_smem_bytes(const LaunchGeom& g) { return (size_t)g.S * 4 * 2 + (size_t)(g.S / 2) * 4; }
 
-// block size: one butterfly per thread up to 1024 threads; for larger trellises as many threads as
-// the shared-memory-limited CTA count per SM leaves room for (K=15: one CTA of 1024 threads per SM)
-static uint32_t generic_block_threads(const LaunchGeom& g) {
-    const uint32_t half = g.S / 2;
-    if (half <= 32) return 32;
-    if (half <= 1024) return half;
-    return 1024;
+template <class OPS, int IN, int BPT>
+static int launch_v2(const LaunchGeom& g, const uint32_t* labels, const void* in, int32_t* path_metric, uint32_t* surv,
+                     uint32_t* final_state, cudaStream_t st) {
+    const size_t smem = (size_t)g.S * 4 * 2;
+    auto k = vit_generic_forward_v2<OPS, IN, BPT>;
+    if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<g.nframes, (g.S / 2) / BPT, smem, st>>>(g, labels, in, path_metric, surv, final_state);
+    VDEC_CUDA(cudaGetLastError());
+    return 0;
 }
 
 template <class OPS, int IN>
 static int generic_forward_launch(const LaunchGeom& g, const uint32_t* labels, const void* in, int32_t* path_metric,
                                   uint32_t* surv, uint32_t* final_state, cudaStream_t st) {
-    const size_t smem = generic_smem_bytes(g);
-    const uint32_t nt = generic_block_threads(g);
-    if (g.S / 2 <= nt) {
+    const uint32_t half = g.S / 2;
+    if (half < 64) {                 // tiny trellises: one (partly idle) warp or two per frame, simple path
+        const size_t smem = generic_smem_bytes(g);
         auto k = vit_generic_forward<OPS, IN, true>;
-        if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<g.nframes, nt, smem, st>>>(g, labels, in, path_metric, surv, final_state);
-    } else {
-        auto k = vit_generic_forward<OPS, IN, false>;
-        if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<g.nframes, nt, smem, st>>>(g, labels, in, path_metric, surv, final_state);
+        k<<<g.nframes, half < 32 ? 32 : half, smem, st>>>(g, labels, in, path_metric, surv, final_state);
+        VDEC_CUDA(cudaGetLastError());
+        return 0;
     }
-    VDEC_CUDA(cudaGetLastError());
-    return 0;
+    // butterflies per thread: tuned on B200 (tools/bench_configs.py); VDEC_GENERIC_BPT overrides
+    uint32_t bpt = half <= 128 ? 2 : half <= 1024 ? 4 : 8;
+    if (const char* e = getenv("VDEC_GENERIC_BPT")) bpt = (uint32_t)atoi(e);
+    while (bpt > 1 && half / bpt < 32) bpt >>= 1;
+    while (half / bpt > 1024) bpt <<= 1;
+    switch (bpt) {
+        case 1: return launch_v2<OPS, IN, 1>(g, labels, in, path_metric, surv, final_state, st);
+        case 2: return launch_v2<OPS, IN, 2>(g, labels, in, path_metric, surv, final_state, st);
+        case 4: return launch_v2<OPS, IN, 4>(g, labels, in, path_metric, surv, final_state, st);
+        case 8: return launch_v2<OPS, IN, 8>(g, labels, in, path_metric, surv, final_state, st);
+        default: set_error("unsupported butterflies-per-thread %u", bpt); return -1;
+    }
 }
 
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,

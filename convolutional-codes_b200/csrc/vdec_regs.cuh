@@ -37,6 +37,10 @@ template <int K_, int N_, uint64_t P0_, uint64_t P1_, uint64_t P2_, bool REF_>
 struct CodeDef {
     static constexpr int K = K_, N = N_, B = K_ - 1, S = 1 << (K_ - 1), M = 1 << N_;
     static constexpr int NW = (S + 31) / 32;
+    // resident CTAs per SM the register budget is cut for.  Measured (tools/bench_configs.py, A/B of
+    // builds): labellings with fewer shared candidate sums, and n = 3, spill at 128 registers and run
+    // 5 % faster with 168 registers and 3 CTAs; the reference-labelled (171,133) code prefers 4.
+    static constexpr int kMinBlocks = (K_ == 7 && !(N_ == 2 && REF_)) ? 3 : 4;
     VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {
         const uint64_t p[3] = {P0_, P1_, P2_};
         return branch_label(K_, N_, p, REF_, s, i);
@@ -364,7 +368,7 @@ template <int M, int B> struct FeederOf<HardU16, M, B> { using type = HardDirect
 constexpr int kTraceChunk = 16;     // survivor words prefetched per traceback chunk
 
 template <class CD, class MP>
-__global__ void __launch_bounds__(kRegsThreads, 4)
+__global__ void __launch_bounds__(kRegsThreads, (MP::kPacked ? CD::kMinBlocks : 4))
 vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
                 uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words) {
     using MT = typename MP::T;
