@@ -32,6 +32,8 @@ EXPORTS = {
     "vdec_decode_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "vdec_decode_iq_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "vdec_decode_iq_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "vdec_stream_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.c_void_p, C.c_void_p]),
     "vdec_sync": (C.c_int, [C.c_void_p]),
     "vdec_launch_count": (C.c_uint64, [C.c_void_p]),
     "vdec_count_errors_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

@@ -38,6 +38,8 @@ struct vdec_priv {
     size_t stage_frames;      // capacity of the host pipeline buffers, in frames
     float* met[3];            // demapped-metric staging for the raw-I/Q entry, per scratch slot
     size_t met_frames[3];
+    uint8_t* stream_tmp;      // per-block outputs of the sliding-window decoder before stitching
+    size_t stream_tmp_bytes;
     float* iq_dev[2];         // device staging of host I/Q, per pipeline stage
     uint8_t* iq_out[2];       // and of the decoded output
     size_t iq_frames;
@@ -45,9 +47,9 @@ struct vdec_priv {
 
 static vdec_priv* priv(vdec_t* h) { return reinterpret_cast<vdec_priv*>(h); }
 
-static int ensure_scratch(vdec_priv* p, int slot, uint32_t frames) {
+static int ensure_scratch(vdec_priv* p, int slot, const vd::LaunchGeom& geom, uint32_t frames) {
     vdec* h = &p->base;
-    vd::LaunchGeom g = h->geom;
+    vd::LaunchGeom g = geom;
     g.nframes = frames;
     const size_t need = h->regs2 ? vd::regs2_bytes(h->regs2, g) : h->regs ? h->regs->surv_bytes(g) : vd::generic_surv_bytes(g);
     if (need <= p->sc.bytes[slot]) return 0;
@@ -81,17 +83,20 @@ static int decode_iq_on(vdec_priv* p, int slot, const float* iq_dev, uint64_t nf
     return 0;
 }
 
-static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframes, uint8_t* out_dev, int32_t* pm_dev,
-                     cudaStream_t st) {
+// decode `nframes` frames of geometry `geom` (geom.T steps each, starts geom.stride_steps apart)
+static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const void* in_dev, uint64_t nframes,
+                       uint8_t* out_dev, int32_t* pm_dev, cudaStream_t st) {
     vdec* h = &p->base;
-    const size_t ib = vd::in_bytes_per_frame(h);
+    const size_t step_bytes = vd::in_bytes_per_frame(h) / h->geom.T;
     uint64_t done = 0;
     while (done < nframes) {
         const uint32_t n = (uint32_t)((nframes - done < h->max_frames) ? (nframes - done) : h->max_frames);
-        if (ensure_scratch(p, slot, n) != 0) return -1;
-        vd::LaunchGeom g = h->geom;
+        if (ensure_scratch(p, slot, geom, n) != 0) return -1;
+        vd::LaunchGeom g = geom;
         g.nframes = n;
-        const void* in = static_cast<const uint8_t*>(in_dev) + done * ib;
+        if (geom.init_all_from != 0xFFFFFFFFu)       // the index is relative to the first frame of the call
+            g.init_all_from = geom.init_all_from > done ? (uint32_t)(geom.init_all_from - done) : 0u;
+        const void* in = static_cast<const uint8_t*>(in_dev) + done * geom.stride_steps * step_bytes;
         uint8_t* out = out_dev + done * g.out_bytes;
         int32_t* pm = pm_dev ? pm_dev + done : nullptr;
         int rc;
@@ -103,6 +108,11 @@ static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframe
         done += n;
     }
     return 0;
+}
+
+static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframes, uint8_t* out_dev, int32_t* pm_dev,
+                     cudaStream_t st) {
+    return decode_geom(p, slot, p->base.geom, in_dev, nframes, out_dev, pm_dev, st);
 }
 
 static const char* metric_tag(uint32_t metric) {
@@ -158,6 +168,7 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
     g.K = cfg->constr_len; g.n = cfg->symlen_out; g.L = cfg->block_len;
     g.S = 1u << (g.K - 1); g.T = g.L + g.K - 1; g.M = 1u << g.n;
     g.out_bytes = (g.T + 7) / 8; g.nw = (g.S + 31) / 32; g.nframes = 0;
+    g.stride_steps = g.T; g.init_all_from = 0xFFFFFFFFu;
 
     // trellis labels from the caller's polynomials (read now: the pointer is only borrowed, viterbi-decoder.c:169)
     const bool quirk = cfg->parity == VDEC_PARITY_REF;
@@ -207,6 +218,7 @@ void vdec_destroy(vdec_t* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 3; ++i) if (p->sc.p[i]) cudaFree(p->sc.p[i]);
     for (int i = 0; i < 3; ++i) if (p->met[i]) cudaFree(p->met[i]);
+    if (p->stream_tmp) cudaFree(p->stream_tmp);
     for (int i = 0; i < 2; ++i) { if (p->iq_dev[i]) cudaFree(p->iq_dev[i]); if (p->iq_out[i]) cudaFree(p->iq_out[i]); }
     for (int i = 0; i < 2; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
@@ -358,6 +370,56 @@ int vdec_decode_iq_host(vdec_t* h, const float* iq_host, uint64_t nframes, uint8
     VDEC_CUDA(cudaStreamSynchronize(h->streams[0]));
     VDEC_CUDA(cudaStreamSynchronize(h->streams[1]));
     return 0;
+}
+
+// One window launch of the sliding-window decoder: `nblk` blocks of T steps whose starts are `stride` steps apart,
+// decoded into the temporary buffer, then bytes [skip/8, skip/8 + keep_bytes) of each block are appended to `out`.
+static int stream_pass(vdec_priv* p, const uint8_t* in, size_t step_bytes, uint64_t start_step, uint64_t nblk, uint32_t T,
+                       uint32_t stride, bool known_first, uint32_t skip_bits, uint64_t keep_bytes, uint64_t last_keep_bytes,
+                       uint8_t* out, cudaStream_t st) {
+    vdec* h = &p->base;
+    if (nblk == 0) return 0;
+    vd::LaunchGeom g = h->geom;
+    g.T = T; g.L = T - (g.K - 1 < T ? g.K - 1 : 0); g.out_bytes = (T + 7) / 8;
+    g.stride_steps = stride; g.init_all_from = known_first ? 1u : 0u;
+    const size_t need = nblk * g.out_bytes;
+    if (need > p->stream_tmp_bytes) {
+        if (p->stream_tmp) { VDEC_CUDA(cudaFree(p->stream_tmp)); p->stream_tmp = nullptr; p->stream_tmp_bytes = 0; }
+        VDEC_CUDA(cudaMalloc(&p->stream_tmp, need));
+        p->stream_tmp_bytes = need;
+    }
+    if (decode_geom(p, 0, g, in + start_step * step_bytes, nblk, p->stream_tmp, nullptr, st) != 0) return -1;
+    h->launches += 1;
+    return vd::stitch_launch(p->stream_tmp, g.out_bytes, skip_bits / 8, nblk, keep_bytes, last_keep_bytes, out, st);
+}
+
+int vdec_stream_decode_device(vdec_t* h, const void* in_dev, uint64_t nsteps, uint32_t block_steps, uint32_t depth,
+                              uint32_t flags, uint8_t* out_dev, void* cuda_stream) {
+    if (!h || !in_dev || !out_dev) { vd::set_error("vdec_stream_decode_device: null argument"); return -1; }
+    if (block_steps < 8 || (block_steps % 8) || (depth % 8)) { vd::set_error("block_steps and depth must be multiples of 8"); return -1; }
+    if (depth > block_steps) { vd::set_error("depth must not exceed block_steps"); return -1; }
+    if ((uint64_t)block_steps + 2ull * depth > 8192) { vd::set_error("block_steps + 2*depth must not exceed 8192"); return -1; }
+    if (nsteps == 0) return 0;
+    vdec_priv* p = priv(h);
+    VDEC_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const uint8_t* in = static_cast<const uint8_t*>(in_dev);
+    const size_t step_bytes = vd::in_bytes_per_frame(h) / h->geom.T;
+    const bool known = (flags & VDEC_STREAM_START_KNOWN) != 0;
+    const uint64_t Lb = block_steps, D = depth;
+    if (nsteps <= Lb + 2 * D) {                                  // short stream: one window, exact
+        return stream_pass(p, in, step_bytes, 0, 1, (uint32_t)nsteps, (uint32_t)nsteps, known, 0, 0, (nsteps + 7) / 8, out_dev, st);
+    }
+    const uint64_t nfull = (nsteps - D) / Lb;                    // windows that deliver a full block of Lb bits
+    // first window: starts with the stream (no warm-up), D steps of look-ahead
+    if (stream_pass(p, in, step_bytes, 0, 1, (uint32_t)(Lb + D), (uint32_t)Lb, known, 0, 0, Lb / 8, out_dev, st) != 0) return -1;
+    // interior windows: D steps warm-up (start state unknown), Lb payload, D look-ahead; starts Lb apart
+    if (nfull > 1 && stream_pass(p, in, step_bytes, Lb - D, nfull - 1, (uint32_t)(Lb + 2 * D), (uint32_t)Lb, false, (uint32_t)D,
+                                 Lb / 8, Lb / 8, out_dev + Lb / 8, st) != 0) return -1;
+    // last window: runs to the end of the stream, traced back from the best final state (viterbi-decoder.c:72-79)
+    const uint64_t s0 = nfull * Lb - D, rest_bits = nsteps - nfull * Lb;
+    return stream_pass(p, in, step_bytes, s0, 1, (uint32_t)(nsteps - s0), (uint32_t)(nsteps - s0), false, (uint32_t)D, 0,
+                       (rest_bits + 7) / 8, out_dev + nfull * (Lb / 8), st);
 }
 
 int vdec_sync(vdec_t* h) {

@@ -69,13 +69,13 @@ vit_generic_forward(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, cons
     const uint32_t half = g.S >> 1, nw = g.nw, T_ = g.T, M = g.M;
     uint32_t* sv = surv + (size_t)f * T_ * nw;
 
-    for (uint32_t s = tid; s < g.S; s += nt) pm0[s] = (s == 0) ? T(0) : OPS::unreachable();          // :215-218
+    for (uint32_t s = tid; s < g.S; s += nt) pm0[s] = (s == 0 || f >= g.init_all_from) ? T(0) : OPS::unreachable();          // :215-218
     if constexpr (!ONE_EACH) for (uint32_t m = tid; m < half; m += nt) lab[m] = __ldg(bfly_labels + m);
 
     // threads 0..M-1 publish the branch metrics one step ahead of their use
-    const float* in_f = static_cast<const float*>(in_v) + (size_t)f * T_ * M + tid;
-    const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * T_;
-    const uint8_t* in_q = static_cast<const uint8_t*>(in_v) + (size_t)f * T_ * M + tid;
+    const float* in_f = static_cast<const float*>(in_v) + (size_t)f * g.stride_steps * M + tid;
+    const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * g.stride_steps;
+    const uint8_t* in_q = static_cast<const uint8_t*>(in_v) + (size_t)f * g.stride_steps * M + tid;
     const bool stager = tid < M;
     auto stage_bm = [&](uint32_t t) {
         if (stager && t < T_) {
@@ -186,12 +186,12 @@ vit_generic_forward_v2(LaunchGeom g, const uint32_t* __restrict__ bfly_labels, c
         const uint32_t lb = __ldg(bfly_labels + i * nt + tid);
         l00[i] = lb & 0xFF; l01[i] = (lb >> 8) & 0xFF; l10[i] = (lb >> 16) & 0xFF; l11[i] = lb >> 24;
     }
-    for (uint32_t s = tid; s < g.S; s += nt) pm0[s] = (s == 0) ? T(0) : OPS::unreachable();          // :215-218
+    for (uint32_t s = tid; s < g.S; s += nt) pm0[s] = (s == 0 || f >= g.init_all_from) ? T(0) : OPS::unreachable();          // :215-218
 
     const bool stager = tid < M;
-    const float* in_f = static_cast<const float*>(in_v) + (size_t)f * T_ * M + tid;
-    const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * T_;
-    const uint8_t* in_q = static_cast<const uint8_t*>(in_v) + (size_t)f * T_ * M + tid;
+    const float* in_f = static_cast<const float*>(in_v) + (size_t)f * g.stride_steps * M + tid;
+    const uint8_t* in_b = static_cast<const uint8_t*>(in_v) + (size_t)f * g.stride_steps;
+    const uint8_t* in_q = static_cast<const uint8_t*>(in_v) + (size_t)f * g.stride_steps * M + tid;
     auto stage_bm = [&](uint32_t t, T* dst) {                   // step t's metrics, one step ahead of their use
         if (stager) {
             const uint32_t tc = t < T_ ? t : T_ - 1;

@@ -26,6 +26,10 @@ struct LaunchGeom {
     uint32_t out_bytes;      // (T+7)/8
     uint32_t nw;             // survivor words (32 decisions each) per trellis step
     uint32_t nframes;        // frames in this launch
+    uint32_t stride_steps;   // trellis steps between the starts of consecutive frames in the input
+                             // (T for packed frames; smaller for overlapping windows of one stream)
+    uint32_t init_all_from;  // frames with index >= this start with ALL states at metric 0 (unknown start
+                             // state, sliding-window blocks); 0xFFFFFFFF = every frame starts in state 0
 };
 
 // ---- code-specialised register kernels (vdec_regs.cu) -------------------------------------
@@ -61,6 +65,8 @@ size_t generic_smem_bytes(const LaunchGeom& g);
 // ---- aux kernels (vdec_synth.cu) ---------------------------------------------------------------
 int count_errors_launch(const uint8_t* dec, const uint8_t* payload, uint64_t nframes, uint32_t L,
                         uint32_t out_bytes, uint64_t* counters, cudaStream_t st);
+int stitch_launch(const uint8_t* tmp, uint32_t row_bytes, uint32_t skip_bytes, uint64_t nblk, uint64_t keep_bytes,
+                  uint64_t last_keep_bytes, uint8_t* out, cudaStream_t st);
 int demap_launch(uint32_t n, const float* iq, uint64_t nsym, float* metrics, cudaStream_t st);
 int synth_awgn_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t nframes, uint64_t first_frame,
                       uint64_t seed, float sigma, uint8_t* payload, float* metrics, float* iq, cudaStream_t st);

@@ -370,7 +370,8 @@ constexpr int kTraceChunk = 16;     // survivor words prefetched per traceback c
 template <class CD, class MP>
 __global__ void __launch_bounds__(kRegsThreads, (MP::kPacked ? CD::kMinBlocks : 4))
 vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
-                uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words) {
+                uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words,
+                uint32_t stride_steps, uint32_t init_all_from) {
     using MT = typename MP::T;
     using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
     using SW = typename SurvWord<CD::NW>::type;
@@ -391,12 +392,13 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     unsigned char* my_smem = s_raw + warp * warp_smem;
 
     Feeder feed;
-    feed.init(my_smem, lane, in + (size_t)fr * T * step_elems, T);
+    feed.init(my_smem, lane, in + (size_t)fr * stride_steps * step_elems, T);
 
     MT r[S];
     r[0] = 0;                                        // decoder_reset: state 0 starts at metric 0 (:215)
+    const MT rest = (f >= init_all_from) ? MT(0) : MP::init_rest();      // sliding-window blocks: start state unknown
 #pragma unroll
-    for (int s = 1; s < S; ++s) r[s] = MP::init_rest();
+    for (int s = 1; s < S; ++s) r[s] = rest;
     [[maybe_unused]] uint64_t rp[S / 2];             // packed mode: physical registers (2q, 2q+1) as one pair
     if constexpr (MP::kPacked) {
 #pragma unroll
@@ -521,7 +523,7 @@ int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path
     if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (g.nframes + kRegsThreads - 1) / kRegsThreads;
     kern<<<blocks, kRegsThreads, smem, st>>>(static_cast<const typename MP::In*>(in), out, path_metric, surv,
-                                              g.nframes, g.T, g.out_bytes, stage_words);
+                                              g.nframes, g.T, g.out_bytes, stage_words, g.stride_steps, g.init_all_from);
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }

@@ -107,7 +107,8 @@ constexpr int kTrace2Chunk = 8;
 template <class CD, int MODE>
 __global__ void __launch_bounds__(kRegsThreads, 4)
 vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
-                 uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words) {
+                 uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words,
+                 uint32_t init_all_from) {
     constexpr int S = CD::S, B = CD::B, M = CD::M, NW = Surv2<S>::NW;
     using SV = typename SurvVec<NW>::type;
     extern __shared__ __align__(16) unsigned char s_raw[];      // output staging: [warp][64 rows][stage_words]
@@ -122,8 +123,9 @@ vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32
 
     uint32_t r[S];
     r[0] = 0;                                                   // :225
+    const uint32_t rest = (fA >= init_all_from ? 0u : 0x8000u) | (fB >= init_all_from ? 0u : 0x80000000u);
 #pragma unroll
-    for (int s = 1; s < S; ++s) r[s] = kBig2;                   // unreachable (:226-228)
+    for (int s = 1; s < S; ++s) r[s] = rest;                    // unreachable (:226-228) unless the start is unknown
 
     uint32_t dw[NW], bm[M];
     uint2 xn = __ldg(src);
@@ -238,7 +240,7 @@ vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32
 constexpr int kPackSteps = 64;
 template <int MODE>
 __global__ void __launch_bounds__(256)
-pack2_kernel(const uint8_t* __restrict__ in, uint2* __restrict__ tin, uint32_t nframes, uint32_t T) {
+pack2_kernel(const uint8_t* __restrict__ in, uint2* __restrict__ tin, uint32_t nframes, uint32_t T, uint32_t stride) {
     __shared__ uint32_t tile[64][kPackSteps + 1];
     const uint32_t gw = blockIdx.y, t0 = blockIdx.x * kPackSteps, tid = threadIdx.x;
     const uint32_t steps = min((uint32_t)kPackSteps, T - t0);
@@ -247,8 +249,8 @@ pack2_kernel(const uint8_t* __restrict__ in, uint2* __restrict__ tin, uint32_t n
         uint32_t f = gw * 64 + row;
         if (f >= nframes) f = nframes - 1;                       // an odd tail shadows the last frame
         if (c < steps) {
-            if constexpr (MODE == kModeHard) tile[row][c] = in[(size_t)f * T + t0 + c];
-            else tile[row][c] = __ldg(reinterpret_cast<const uint32_t*>(in) + (size_t)f * T + t0 + c);
+            if constexpr (MODE == kModeHard) tile[row][c] = in[(size_t)f * stride + t0 + c];
+            else tile[row][c] = __ldg(reinterpret_cast<const uint32_t*>(in) + (size_t)f * stride + t0 + c);
         }
     }
     __syncthreads();
@@ -279,7 +281,7 @@ int regs2_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* pat
     uint2* tin = reinterpret_cast<uint2*>(scratch);
     uint32_t* surv = reinterpret_cast<uint32_t*>(tin + warps * g.T * 32);
     pack2_kernel<MODE><<<dim3((g.T + kPackSteps - 1) / kPackSteps, (unsigned)warps), 256, 0, st>>>(
-        static_cast<const uint8_t*>(in), tin, g.nframes, g.T);
+        static_cast<const uint8_t*>(in), tin, g.nframes, g.T, g.stride_steps);
     VDEC_CUDA(cudaGetLastError());
     uint32_t stage_words = (g.out_bytes + 3) / 4;
     if ((stage_words & 1) == 0) ++stage_words;
@@ -287,7 +289,7 @@ int regs2_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* pat
     auto kern = vit_regs2_kernel<CD, MODE>;
     if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (uint32_t)((npairs + kRegsThreads - 1) / kRegsThreads);
-    kern<<<blocks, kRegsThreads, smem, st>>>(tin, out, path_metric, surv, g.nframes, g.T, g.out_bytes, stage_words);
+    kern<<<blocks, kRegsThreads, smem, st>>>(tin, out, path_metric, surv, g.nframes, g.T, g.out_bytes, stage_words, g.init_all_from);
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }

@@ -163,6 +163,18 @@ __global__ void count_errors_kernel(const uint8_t* __restrict__ dec, const uint8
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters, (unsigned long long)nframes * L);
 }
 
+// sliding-window stitching: block b contributes bytes [skip, skip + keep) of its output row (the last block
+// `last_keep` bytes) to the contiguous decoded stream
+__global__ void stitch_kernel(const uint8_t* __restrict__ tmp, uint32_t row_bytes, uint32_t skip, uint64_t nblk, uint64_t keep,
+                              uint64_t last_keep, uint8_t* __restrict__ out) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t total = (nblk - 1) * keep + last_keep;
+    if (i >= total) return;
+    const uint64_t b = keep ? (i / keep < nblk - 1 ? i / keep : nblk - 1) : 0;
+    const uint64_t j = i - b * keep;
+    out[i] = tmp[b * row_bytes + skip + j];
+}
+
 inline unsigned grid_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -172,6 +184,15 @@ int count_errors_launch(const uint8_t* dec, const uint8_t* payload, uint64_t nfr
     if (nframes == 0) return 0;
     count_errors_kernel<<<grid_for(nframes, 256), 256, 0, st>>>(dec, payload, nframes, L, out_bytes,
                                                                 reinterpret_cast<unsigned long long*>(counters));
+    VDEC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int stitch_launch(const uint8_t* tmp, uint32_t row_bytes, uint32_t skip_bytes, uint64_t nblk, uint64_t keep_bytes,
+                  uint64_t last_keep_bytes, uint8_t* out, cudaStream_t st) {
+    const uint64_t total = (nblk - 1) * keep_bytes + last_keep_bytes;
+    if (total == 0) return 0;
+    stitch_kernel<<<grid_for(total, 256), 256, 0, st>>>(tmp, row_bytes, skip_bytes, nblk, keep_bytes, last_keep_bytes, out);
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }

@@ -165,6 +165,20 @@ class BatchDecoder:
             raise VdecError(_lib.last_error())
         return out
 
+    # -- sliding-window decoding of one long / unterminated stream -----------------------------------------
+    def decode_stream(self, x, block_steps: int = 1024, depth: int = 128, start_known: bool = True, stream=None):
+        """x: [nsteps, M] float32 (soft), [nsteps, M] uint8 (quantised) or [nsteps] uint8 (hard), CUDA.
+        Returns uint8 [(nsteps+7)//8]: decoded bit per trellis step, MSB-first."""
+        import torch
+        assert x.is_cuda and x.is_contiguous()
+        nsteps = x.shape[0]
+        out = torch.empty(((nsteps + 7) // 8,), dtype=torch.uint8, device=x.device)
+        rc = self.lib.vdec_stream_decode_device(self.h, C.c_void_p(x.data_ptr()), nsteps, block_steps, depth,
+                                                1 if start_known else 0, C.c_void_p(out.data_ptr()), self._stream_ptr(stream))
+        if rc != 0:
+            raise VdecError(_lib.last_error())
+        return out
+
     def sync(self):
         if self.lib.vdec_sync(self.h) != 0:
             raise VdecError(_lib.last_error())

@@ -110,6 +110,19 @@ int vdec_decode_host(vdec_t* h, const void* in_host, uint64_t nframes, uint8_t* 
  * bytes that cross PCIe per decoded bit (8.2 instead of 16.2 at K=7, n=2).  Soft metric only. */
 int vdec_decode_iq_device(vdec_t* h, const float* iq_dev, uint64_t nframes, uint8_t* out_dev, void* cuda_stream);
 int vdec_decode_iq_host(vdec_t* h, const float* iq_host, uint64_t nframes, uint8_t* out_host);
+/* Sliding-window decoding of ONE long or unterminated symbol stream (north_star piece 4).
+ * The reference keeps the survivors of the whole frame (viterbi-decoder.c:183) and cannot do this.  The stream
+ * of `nsteps` trellis steps (same per-step format as the batched input) is decoded as overlapping windows of
+ * `block_steps` payload steps with `depth` extra steps on either side (warm-up from an unknown start state /
+ * traceback convergence), all windows in parallel, and the payload bits are stitched into
+ * out_dev[(nsteps+7)/8] (MSB-first, bit t = step t).  Equal to full-length decoding whenever the survivor
+ * paths merge within `depth` steps (depth >= ~10*K in practice); the final state is the lowest-index argmin
+ * as in viterbi-decoder.c:72-79.  Needs a non-catastrophic code (codebook entries 0 and 3 are catastrophic: their
+ * polynomials share the factor 1+D and survivor paths need not merge).  block_steps, depth: multiples of 8,
+ * depth <= block_steps, block_steps + 2*depth <= 8192. */
+enum vdec_stream_flags { VDEC_STREAM_START_KNOWN = 1u /* the stream begins in state 0 (a tail-terminated frame) */ };
+int vdec_stream_decode_device(vdec_t* h, const void* in_dev, uint64_t nsteps, uint32_t block_steps, uint32_t depth,
+                              uint32_t flags, uint8_t* out_dev, void* cuda_stream);
 int vdec_sync(vdec_t* h);
 /* number of this library's kernels launched through `h` so far */
 uint64_t vdec_launch_count(const vdec_t* h);

@@ -290,3 +290,43 @@ def test_quantised_mode_vs_oracle(cc, orc, torch_cuda, key, L, F, qmax, parity):
     assert np.array_equal(out, exp), name
     out, name = _decode_quant(cc, torch_cuda, code, parity, q, 0, flags=cc.FORCE_GENERIC)
     assert name.startswith("generic_soft_u8") and np.array_equal(out, exp)
+
+
+# (codebook 0 and 3 are catastrophic codes — gcd of their polynomials is 1+D — so their survivor paths need not
+# merge and windowed decoding does not apply to them; the test uses the non-catastrophic ones)
+@pytest.mark.parametrize("key,metric", [("k7r12", "soft"), ("cb2", "soft"), ("k7r12", "hard"), ("k9", "soft")])
+def test_sliding_window_stream_equals_full_length_decoding(cc, orc, torch_cuda, key, metric):
+    """vdec_stream_decode_device: one long tail-terminated frame decoded as overlapping windows must equal the
+    full-length decode (oracle = reference algorithm with the whole survivor matrix) once the window depth
+    exceeds the survivor merge depth; short streams take the single-window path and are exact by construction."""
+    torch = torch_cuda
+    L = 30000 if key != "k9" else 6000
+    code = _get(cc, key, L)
+    oc = ocode(code, 1)
+    if metric == "soft":
+        _, x = make_soft_inputs(orc, oc, 1, 0.5, seed=L)
+        exp = orc.decode_soft(oc, x)[0]
+        dec = cc.BatchDecoder(code, cc.SOFT_F32, cc.PARITY_LINEAR)
+        xd = torch.from_numpy(x[0]).cuda()
+    else:
+        _, x = make_hard_inputs(orc, oc, 1, 0.03, seed=L)
+        exp = orc.decode_hard(oc, x)[0][0]
+        dec = cc.BatchDecoder(code, cc.HARD_U16, cc.PARITY_LINEAR)
+        xd = torch.from_numpy(x[0]).cuda()
+    for block, depth in ((1024, 512), (4096, 256), (512, 512)):
+        got = dec.decode_stream(xd, block, depth).cpu().numpy()
+        assert got.shape == exp.shape
+        assert np.array_equal(got, exp), (block, depth, int(np.unpackbits(got ^ exp).sum()))
+    # a stream shorter than one window: single pass, identical to the batched call
+    short = xd[:700].contiguous()
+    sc = code.with_block_len(700 - (code.K - 1))
+    d2 = cc.BatchDecoder(sc, dec.metric, cc.PARITY_LINEAR)
+    ref = d2.decode(short.unsqueeze(0))
+    ref = (ref[0] if isinstance(ref, tuple) else ref)[0]
+    assert torch.equal(dec.decode_stream(short, 1024, 128), ref)
+    with pytest.raises(cc.VdecError):
+        dec.decode_stream(xd, 512, 1024)                               # depth > block is refused
+    # unknown start state: still converges after the first `depth` steps of the stream
+    got = dec.decode_stream(xd, 1024, 512, start_known=False).cpu().numpy()
+    assert np.array_equal(got[64:], exp[64:])
+    dec.close(); d2.close()

@@ -37,6 +37,27 @@ def main():
         ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 16384 // q, 0),
         ("C4 soft K15 L1024", C.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 1024 // q, 0),
     ]
+    if not args.only or args.only in "stream K7 sliding-window":
+        # one unterminated stream of 2^28 steps, windows of 1024 payload + 2x128 overlap steps
+        code = C.K7_R12
+        nsteps = (1 << 28) // q
+        dec = cc.BatchDecoder(code, cc.SOFT_F32, cc.PARITY_LINEAR)
+        nb = nsteps // code.T
+        _, x = dec.synth_awgn(nb, 0, 1, cc.awgn_sigma(4.0))       # frames back to back = a long symbol stream
+        x = x.reshape(nb * code.T, code.M)
+        for blk, dep in ((1024, 128), (4096, 128)):
+            dec.decode_stream(x, blk, dep, start_known=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                dec.decode_stream(x, blk, dep, start_known=True)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            print(json.dumps({"case": f"stream K7 sliding-window block={blk} depth={dep}", "kernel": dec.kernel_name,
+                              "steps": x.shape[0], "ms": round(ms, 3), "gbit_s": round(x.shape[0] / ms / 1e6, 3)}), flush=True)
+        dec.close(); del x
+        torch.cuda.empty_cache()
     for name, code, metric, parity, F, flags in cases:
         if args.only and args.only not in name:
             continue
