@@ -31,6 +31,11 @@
 
 #include "vdec_internal.h"
 
+// tuning knobs for A/B builds (tools/build_variant.py)
+#ifndef VDEC_MINB_REF
+#define VDEC_MINB_REF 4
+#endif
+
 namespace vd {
 
 template <int K_, int N_, uint64_t P0_, uint64_t P1_, uint64_t P2_, bool REF_>
@@ -40,7 +45,7 @@ struct CodeDef {
     // resident CTAs per SM the register budget is cut for.  Measured (tools/bench_configs.py, A/B of
     // builds): labellings with fewer shared candidate sums, and n = 3, spill at 128 registers and run
     // 5 % faster with 168 registers and 3 CTAs; the reference-labelled (171,133) code prefers 4.
-    static constexpr int kMinBlocks = (K_ == 7 && !(N_ == 2 && REF_)) ? 3 : 4;
+    static constexpr int kMinBlocks = (K_ == 7 && !(N_ == 2 && REF_)) ? 3 : VDEC_MINB_REF;
     VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {
         const uint64_t p[3] = {P0_, P1_, P2_};
         return branch_label(K_, N_, p, REF_, s, i);
@@ -287,54 +292,63 @@ struct SoftRing {
     static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * kStepBytes;   // K=7, n=2: 9 KB
     static_assert(M == 4 || M == 8, "soft ring feeder supports n = 2, 3");
 
-    uint32_t base;        // shared-window address of this lane's first piece
-    const float* src;     // this lane's frame row
-    uint32_t T;
-    uint32_t grp;         // group (= period) being consumed
-    uint32_t slot0;       // first ring slot of that group
+    static constexpr uint32_t kGroupBytes = (uint32_t)G * kPieces * 512;   // ring bytes of one group (all 32 lanes)
 
-    __device__ __forceinline__ void prefetch_group(uint32_t g) const {
-        const uint32_t s0 = (g % NG) * G;
+    uint32_t base;        // shared-window address of this lane's first piece
+    uint32_t T;
+    const float* nextp;   // first step of the next group to prefetch (this lane's frame row)
+    uint32_t next_t;      // its step index
+    uint32_t woff;        // ring byte offset where that group goes
+    uint32_t roff;        // ring byte offset of the group being consumed
+
+    // Everything is kept incrementally (pointer, step, ring offsets) and the copies of a full group use
+    // immediate offsets, so a period pays G*kPieces LDGSTS plus a handful of adds for its input.
+    __device__ __forceinline__ void prefetch_next() {
+        const uint32_t dst = base + woff;
+        if (next_t + G <= T) {
+            static_for<0, G * kPieces>([&](auto ic) {
+                constexpr int I = decltype(ic)::value, s = I / kPieces, c = I % kPieces;
+                asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;"
+                             ::"r"(dst), "l"(nextp), "n"((s * kPieces + c) * 512), "n"((s * M + c * 4) * 4) : "memory");
+            });
+        } else {
 #pragma unroll
-        for (int s = 0; s < G; ++s) {
-            const uint32_t t = g * G + s;
-            if (t < T) {
+            for (int s = 0; s < G; ++s)
+                if (next_t + s < T) {
 #pragma unroll
-                for (int c = 0; c < kPieces; ++c) {
-                    const uint32_t dst = base + (((s0 + s) * kPieces + c) * 32) * 16;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + (size_t)t * M + c * 4) : "memory");
+                    for (int c = 0; c < kPieces; ++c)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                     ::"r"(dst + (s * kPieces + c) * 512), "l"(nextp + s * M + c * 4) : "memory");
                 }
-            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        nextp += G * M; next_t += G;
+        woff = (woff == (NG - 1) * kGroupBytes) ? 0u : woff + kGroupBytes;
     }
     __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
         base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * 16;
-        src = row; T = steps; grp = 0; slot0 = 0;
-        prefetch_group(0);
-        prefetch_group(1);
+        T = steps; nextp = row; next_t = 0; woff = 0; roff = 0;
+        prefetch_next();
+        prefetch_next();
     }
     // start of a period: keep the ring two groups ahead, make the current group visible
-    __device__ __forceinline__ void begin_period() const {
-        prefetch_group(grp + 2);
+    __device__ __forceinline__ void begin_period() {
+        prefetch_next();
         asm volatile("cp.async.wait_group 2;" ::: "memory");
     }
-    __device__ __forceinline__ void end_period() {
-        ++grp;
-        slot0 = (slot0 == (NG - 1) * G) ? 0 : slot0 + G;
-    }
+    __device__ __forceinline__ void end_period() { roff = (roff == (NG - 1) * kGroupBytes) ? 0u : roff + kGroupBytes; }
     // packed mode: fetch every operand pair (bm[x], bm[y]) that MASK names straight into a 64-bit
     // register pair with two scalar loads.  Volatile so that ptxas neither fuses them into a v4 load
     // (which pins four consecutive registers and costs two MOVs per FADD2 operand) nor drops them.
     template <uint64_t MASK, int PH>
     __device__ __forceinline__ void get_pairs(uint64_t (&bp)[M * M]) const {
-        const uint32_t a = base + ((slot0 + PH) * kPieces * 32) * 16;
+        const uint32_t a = base + roff;
         static_for<0, M * M>([&](auto ic) {
             constexpr int I = decltype(ic)::value, x = I / M, y = I % M;
             if constexpr ((MASK >> I) & 1ull) {
                 float lo, hi;
-                asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(lo) : "r"(a + (x / 4) * 512 + 4 * (x % 4)));
-                asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(hi) : "r"(a + (y / 4) * 512 + 4 * (y % 4)));
+                asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(lo) : "r"(a), "n"((PH * kPieces + x / 4) * 512 + 4 * (x % 4)));
+                asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(hi) : "r"(a), "n"((PH * kPieces + y / 4) * 512 + 4 * (y % 4)));
                 asm("mov.b64 %0, {%1, %2};" : "=l"(bp[I]) : "f"(lo), "f"(hi));
             } else {
                 bp[I] = 0;
@@ -365,7 +379,10 @@ template <class MP, int M, int B> struct FeederOf;
 template <int M, int B> struct FeederOf<SoftF32, M, B> { using type = SoftRing<M, B>; };
 template <int M, int B> struct FeederOf<HardU16, M, B> { using type = HardDirect<M, B>; };
 
-constexpr int kTraceChunk = 16;     // survivor words prefetched per traceback chunk
+#ifndef VDEC_TRACE_CHUNK
+#define VDEC_TRACE_CHUNK 16
+#endif
+constexpr int kTraceChunk = VDEC_TRACE_CHUNK;     // survivor words prefetched per traceback chunk
 
 template <class CD, class MP>
 __global__ void __launch_bounds__(kRegsThreads, (MP::kPacked ? CD::kMinBlocks : 4))

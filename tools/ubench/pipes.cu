@@ -22,13 +22,16 @@ enum { OP_FADD, OP_FADD2, OP_FMNMX, OP_IADD, OP_IMAD, OP_SHF, OP_LOP, OP_SETPSEL
        MIX_ACS_D,   // FADD2 + 2x(FMNMX + FADD(diff) + SHF)
        MIX_ACS_E,   // FADD2 + 2x(FMNMX + IMAD(diff) + SHF)
        MIX_ACS_F,   // 2 FADD + FMNMX + FADD(diff) + SHF
+       MIX_F2_MNMX,   // FADD2 : FMNMX 1:1  -> does FADD2 take one issue slot or two?
+       MIX_F2_MNMX2,  // FADD2 : FMNMX 1:2
+       MIX_F2_FADD,   // FADD2 : FADD 1:1
        NOPS };
 static const char* names[NOPS] = {"FADD", "FADD2", "FMNMX", "IADD3", "IMAD", "SHF", "LOP3", "FSETP+SELP",
   "FADD+FMNMX", "FADD+IADD3", "FADD+IMAD", "FMNMX+IADD3",
   "ACS_A 2FADD+FMNMX+IADD+SHF", "ACS_B 2FADD+FSETP+SELP+@pOR", "ACS_C FADD2+2(FMNMX+IADD+SHF)",
-  "ACS_D FADD2+2(FMNMX+FADDdiff+SHF)", "ACS_E FADD2+2(FMNMX+IMADdiff+SHF)", "ACS_F 2FADD+FMNMX+FADDdiff+SHF"};
+  "ACS_D FADD2+2(FMNMX+FADDdiff+SHF)", "ACS_E FADD2+2(FMNMX+IMADdiff+SHF)", "ACS_F 2FADD+FMNMX+FADDdiff+SHF", "FADD2+FMNMX 1:1", "FADD2+2FMNMX", "FADD2+FADD 1:1"};
 // instructions per chain-iteration for each op
-static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5};
+static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5, 2, 3, 2};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, long long* cyc) {
@@ -94,6 +97,15 @@ __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, lon
         asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(u[i]) : "r"(d0));
         asm volatile("shf.l.wrap.b32 %0, %1, %0, 1;" : "+r"(v[i]) : "r"(d1));
         d[i] = ((unsigned long long)__float_as_uint(n1) << 32) | __float_as_uint(n0);
+      }
+      if (OP == MIX_F2_MNMX || OP == MIX_F2_MNMX2) {
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(c2));
+        asm volatile("min.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i]));
+        if (OP == MIX_F2_MNMX2) asm volatile("max.f32 %0, %0, %1;" : "+f"(g[i]) : "f"(f[i]));
+      }
+      if (OP == MIX_F2_FADD) {
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(c2));
+        asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i]));
       }
       if (OP == MIX_ACS_F) {
         float c0, c1, e0;
