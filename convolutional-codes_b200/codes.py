@@ -74,7 +74,10 @@ def get_code(index: int) -> CodeParam:
 # BASELINE.json configs that are not in the reference codebook
 K7_R12 = CodeParam(2, 7, 1024, (left_align("171", 7), left_align("133", 7)), "K7 (171,133)")
 K7_R13 = CodeParam(3, 7, 1024, (left_align("133", 7), left_align("171", 7), left_align("165", 7)), "K7 (133,171,165)")
+K8_R12 = CodeParam(2, 8, 1024, (left_align("371", 8), left_align("247", 8)), "K8 (371,247)")
 K9_R12 = CodeParam(2, 9, 1024, (left_align("561", 9), left_align("753", 9)), "K9 (561,753)")
+K10_R12 = CodeParam(2, 10, 1024, (left_align("1167", 10), left_align("1545", 10)), "K10 (1167,1545)")
+K11_R12 = CodeParam(2, 11, 1024, (left_align("2335", 11), left_align("3661", 11)), "K11 (2335,3661)")
 K15_R12 = CodeParam(2, 15, 1024, (left_align("46321", 15), left_align("51271", 15)), "K15 (46321,51271)")
 
 # noise scaling of the AWGN driver: sigma = 2^-1/2 * 10^(-EbN0_dB/20)  (AWGN-channel/main.c:153-161)

@@ -55,6 +55,13 @@ int regs2_run(const Regs2Entry* e, const LaunchGeom& g, const void* in, uint8_t*
               uint32_t* scratch, cudaStream_t st);
 size_t regs2_bytes(const Regs2Entry* e, const LaunchGeom& g);
 
+// ---- lane-group register kernels for K = 8 .. 12 (vdec_regsw.cu) -------------------------------------
+struct WideEntry;
+const WideEntry* regsw_find(uint32_t K, uint32_t n, uint32_t metric, const uint8_t* labels);
+const char* regsw_name(const WideEntry* e);
+int regsw_run(const WideEntry* e, const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st);
+size_t regsw_bytes(const WideEntry* e, const LaunchGeom& g);
+
 // ---- generic table-driven kernels (vdec_generic.cu) ----------------------------------------
 // One CTA per frame, path metrics in shared memory, labels from a device table; any K <= 15.
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
@@ -86,6 +93,7 @@ struct vdec {
     uint32_t* bfly_labels_dev;       // [S/2] packed l00 | l01<<8 | l10<<16 | l11<<24
     const vd::RegsEntry* regs;     // non-null => specialised kernel
     const vd::Regs2Entry* regs2;   // non-null => packed 16-bit kernel (takes precedence)
+    const vd::WideEntry* regsw;    // non-null => lane-group register kernel (K = 8 .. 12)
     uint32_t* surv;                  // survivor scratch
     size_t surv_bytes;
     // host-buffer pipeline (vdec_decode_host)

@@ -61,13 +61,15 @@ SOFT_CASES = [  # (code getter, L, frames, sigma)
     ("cb0", 40, 1000, 0.45), ("cb1", 40, 333, 0.5), ("cb2", 57, 129, 0.5), ("cb3", 40, 64, 0.45), ("cb5", 40, 257, 0.6),
     ("k7r12", 1024, 96, 0.446154216921401), ("k7r12", 249, 33, 0.56), ("k7r12", 5, 31, 0.4), ("k7r12", 1, 7, 0.4),
     ("k7r13", 300, 65, 0.6), ("k9", 128, 9, 0.5), ("k15", 40, 2, 0.5),
+    # lane-group register kernels (2, 4, 8, 16 lanes per frame), ragged frame counts and lengths
+    ("k8", 200, 67, 0.5), ("k9", 1024, 41, 0.45), ("k9", 3, 5, 0.5), ("k10", 150, 13, 0.5), ("k11", 97, 7, 0.5),
 ]
 
 
 def _get(cc, key, L):
     table = {"cb0": cc.get_code(0), "cb1": cc.get_code(1), "cb2": cc.get_code(2), "cb3": cc.get_code(3),
-             "cb5": cc.get_code(5), "k7r12": cc.codes.K7_R12, "k7r13": cc.codes.K7_R13, "k9": cc.codes.K9_R12,
-             "k15": cc.codes.K15_R12}
+             "cb5": cc.get_code(5), "k7r12": cc.codes.K7_R12, "k7r13": cc.codes.K7_R13, "k8": cc.codes.K8_R12, "k9": cc.codes.K9_R12,
+             "k10": cc.codes.K10_R12, "k11": cc.codes.K11_R12, "k15": cc.codes.K15_R12}
     return table[key].with_block_len(L)
 
 
@@ -80,7 +82,7 @@ def test_soft_vs_oracle(cc, orc, torch_cuda, key, L, F, sigma, parity):
     exp = orc.decode_soft(oc, met)
     out, name = _decode_soft(cc, torch_cuda, code, parity, met)
     assert np.array_equal(out, exp), f"{name}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
-    if code.K <= 7:   # the table-driven kernel must agree too
+    if code.K <= 11:   # the table-driven kernel must agree too
         out2, name2 = _decode_soft(cc, torch_cuda, code, parity, met, flags=cc.FORCE_GENERIC)
         assert name2.startswith("generic") and np.array_equal(out2, exp)
 

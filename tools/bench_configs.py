@@ -34,7 +34,9 @@ def main():
         ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, (1 << 18) // q, 0),
         ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 18) // q, 0),
         ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),
-        ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 16384 // q, 0),
+        ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, 0),
+        ("C4 soft K9 L1024 ref-labels (table-driven)", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 16384 // q, 0),
+        ("C4 soft K11 L1024", C.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 32768 // q, 0),
         ("C4 soft K15 L1024", C.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 1024 // q, 0),
     ]
     if not args.only or args.only in "stream K7 sliding-window":
