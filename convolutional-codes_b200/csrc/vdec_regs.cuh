@@ -165,7 +165,6 @@ __device__ __forceinline__ float sel_lt(float ce, float co, float& acc, float w)
         : "=f"(dst), "+f"(acc) : "f"(ce), "f"(co), "f"(w));
     return dst;
 }
-
 // decision j of a step lives in accumulator j / 24 with weight 2^(j % 24)
 constexpr int kAccBits = 24;
 VDEC_HD constexpr float acc_weight(uint32_t j) { return (float)(1u << (j % kAccBits)); }
@@ -219,37 +218,38 @@ __device__ __forceinline__ void acs_step_f2(uint64_t (&rp)[CD::S / 2], const uin
 #pragma unroll
     for (int a = 0; a < NA; ++a) da[a] = 0.f;
     if constexpr (PB == 0) {
-#pragma unroll
-        for (int q = 0; q < S / 2; ++q) {
-            const uint32_t u = rotr_bits(2 * q, PH, B), v = u + 1;
-            const uint32_t j0 = u >> 1, j1 = j0 + S / 2;
+        static_for<0, S / 2>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            constexpr uint32_t u = rotr_bits(2 * q, PH, B), v = u + 1;
+            constexpr uint32_t j0 = u >> 1, j1 = j0 + S / 2;
             float e0, o0, e1, o1;
             unpack2(fadd2(rp[q], bp[CD::label(u, 0) * M + CD::label(v, 0)]), e0, o0);
             unpack2(fadd2(rp[q], bp[CD::label(u, 1) * M + CD::label(v, 1)]), e1, o1);
             const float n0 = sel_lt(e0, o0, da[j0 / kAccBits], acc_weight(j0));
             const float n1 = sel_lt(e1, o1, da[j1 / kAccBits], acc_weight(j1));
             rp[q] = pack2(n0, n1);
-        }
+        });
     } else {
-#pragma unroll
-        for (int q = 0; q < S / 2; ++q) {
-            if ((q >> (PB - 1)) & 1) continue;
-            const int q2 = q | (1 << (PB - 1));
-            const uint32_t u0 = rotr_bits(2 * q, PH, B), u1 = rotr_bits(2 * q + 1, PH, B);
-            const uint32_t v0 = u0 + 1, v1 = u1 + 1;
-            const uint32_t ja = u0 >> 1, jb = u1 >> 1;          // input-0 successors; +S/2 for input 1
-            float ea, eb, oa, ob, fa, fb, pa, pb_;
-            unpack2(fadd2(rp[q],  bp[CD::label(u0, 0) * M + CD::label(u1, 0)]), ea, eb);
-            unpack2(fadd2(rp[q2], bp[CD::label(v0, 0) * M + CD::label(v1, 0)]), oa, ob);
-            unpack2(fadd2(rp[q],  bp[CD::label(u0, 1) * M + CD::label(u1, 1)]), fa, fb);
-            unpack2(fadd2(rp[q2], bp[CD::label(v0, 1) * M + CD::label(v1, 1)]), pa, pb_);
-            const float na = sel_lt(ea, oa, da[ja / kAccBits], acc_weight(ja));
-            const float nb = sel_lt(eb, ob, da[jb / kAccBits], acc_weight(jb));
-            const float ma = sel_lt(fa, pa, da[(ja + S / 2) / kAccBits], acc_weight(ja + S / 2));
-            const float mb = sel_lt(fb, pb_, da[(jb + S / 2) / kAccBits], acc_weight(jb + S / 2));
-            rp[q] = pack2(na, nb);
-            rp[q2] = pack2(ma, mb);
-        }
+        static_for<0, S / 2>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            if constexpr (((q >> (PB - 1)) & 1) == 0) {
+                constexpr int q2 = q | (1 << (PB - 1));
+                constexpr uint32_t u0 = rotr_bits(2 * q, PH, B), u1 = rotr_bits(2 * q + 1, PH, B);
+                constexpr uint32_t v0 = u0 + 1, v1 = u1 + 1;
+                constexpr uint32_t ja = u0 >> 1, jb = u1 >> 1;          // input-0 successors; +S/2 for input 1
+                float ea, eb, oa, ob, fa, fb, pa, pb_;
+                unpack2(fadd2(rp[q],  bp[CD::label(u0, 0) * M + CD::label(u1, 0)]), ea, eb);
+                unpack2(fadd2(rp[q2], bp[CD::label(v0, 0) * M + CD::label(v1, 0)]), oa, ob);
+                unpack2(fadd2(rp[q],  bp[CD::label(u0, 1) * M + CD::label(u1, 1)]), fa, fb);
+                unpack2(fadd2(rp[q2], bp[CD::label(v0, 1) * M + CD::label(v1, 1)]), pa, pb_);
+                const float na = sel_lt(ea, oa, da[ja / kAccBits], acc_weight(ja));
+                const float nb = sel_lt(eb, ob, da[jb / kAccBits], acc_weight(jb));
+                const float ma = sel_lt(fa, pa, da[(ja + S / 2) / kAccBits], acc_weight(ja + S / 2));
+                const float mb = sel_lt(fb, pb_, da[(jb + S / 2) / kAccBits], acc_weight(jb + S / 2));
+                rp[q] = pack2(na, nb);
+                rp[q2] = pack2(ma, mb);
+            }
+        });
     }
     acc_to_words<S>(da, dw);
 }
@@ -383,6 +383,7 @@ template <int M, int B> struct FeederOf<HardU16, M, B> { using type = HardDirect
 #define VDEC_TRACE_CHUNK 16
 #endif
 constexpr int kTraceChunk = VDEC_TRACE_CHUNK;     // survivor words prefetched per traceback chunk
+static_assert(kTraceChunk % 16 == 0, "traceback emits 16 output bits per 16 steps");
 
 template <class CD, class MP>
 __global__ void __launch_bounds__(kRegsThreads, (MP::kPacked ? CD::kMinBlocks : 4))
@@ -475,37 +476,55 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     __syncwarp();                                     // ring reads are done before the tile is reused
 
     // ---- traceback (:81-89): decision of state `cur` at step tt, decoded bit = MSB of cur -----
-    // The survivor words of a step do not depend on `cur`, so they are fetched a chunk ahead
-    // (coalesced: 32 lanes x NW words) and only the bit select is on the dependent chain.
-    uint32_t* stage = reinterpret_cast<uint32_t*>(my_smem) + (size_t)lane * stage_words;
+    // The survivor words of a step do not depend on the state, so they are fetched a chunk ahead
+    // (coalesced: 32 lanes x NW words).  The state is kept as an unmasked shift register `h`
+    // (cur = h & (S-1)): the decoded bit of step tt is the decision taken B-1 steps later on the way
+    // back, so bit B-1+i of h at step tt is the decoded bit of step tt+i and 16 output bits fall out
+    // of h every 16 steps without any per-step accumulation.  Dependent chain per step: one variable
+    // shift and one 3-input logic op; the survivor-word select hangs on bit B-1 of cur, known B-1
+    // steps earlier.  Rows are staged at their final out_bytes pitch, so the warp's tile is the
+    // byte image of its 32 contiguous output rows.
+    unsigned char* tile = my_smem;
     if (live) {
         const SW* svw = reinterpret_cast<const SW*>(sv);
+        unsigned char* srow = tile + (size_t)lane * out_bytes;
         SW wc[kTraceChunk], wn[kTraceChunk];
         int base = ((int)T - 1) & ~(kTraceChunk - 1);
 #pragma unroll
         for (int j = 0; j < kTraceChunk; ++j)
             if (base + j < (int)T) wc[j] = __ldcg(svw + (size_t)(base + j) * 32);
-        uint32_t acc = 0;
-        for (; base >= 0; base -= kTraceChunk) {
+        uint32_t h = cur;
+        auto chunk = [&](auto guard) {
+            constexpr bool GUARD = decltype(guard)::value;      // first chunk only: steps >= T do not exist
+#pragma unroll
+            for (int j = kTraceChunk - 1; j >= 0; --j) {
+                const int tt = base + j;
+                if (GUARD && tt >= (int)T) continue;
+                if ((j & 15) == 0) {                             // bits tt .. tt+15 -> bytes tt/8, tt/8+1, MSB-first (:88)
+                    const uint32_t rv = __brev(h >> (B - 1));
+                    srow[tt >> 3] = (unsigned char)(rv >> 24);
+                    if (!GUARD || tt + 8 < (int)T) srow[(tt >> 3) + 1] = (unsigned char)(rv >> 16);
+                }
+                uint32_t word;
+                if constexpr (NW == 1) word = wc[j];
+                else word = (h & 32u) ? wc[j].y : wc[j].x;
+                h = (h << 1) | ((word >> (h & (S - 1) & 31u)) & 1u);   // predecessor (:86)
+            }
+        };
+        auto prefetch = [&]() {
             if (base >= kTraceChunk) {
 #pragma unroll
                 for (int j = 0; j < kTraceChunk; ++j) wn[j] = __ldcg(svw + (size_t)(base - kTraceChunk + j) * 32);
             }
-#pragma unroll
-            for (int j = kTraceChunk - 1; j >= 0; --j) {
-                const int tt = base + j;
-                if (tt < (int)T) {
-                    uint32_t word;
-                    if constexpr (NW == 1) word = wc[j];
-                    else word = (cur & 32) ? wc[j].y : wc[j].x;
-                    const uint32_t d = (word >> (cur & 31)) & 1u;
-                    acc |= (cur >> (B - 1)) << (31 - (tt & 31));      // bit tt -> byte tt/8, bit 7-(tt%8)  (:88)
-                    cur = ((cur << 1) & (S - 1)) | d;                  // predecessor (:86)
-                    if ((tt & 31) == 0) { stage[tt >> 5] = __byte_perm(acc, 0, 0x0123); acc = 0; }
-                }
-            }
+        };
+        prefetch();
+        chunk(std::true_type{});
+        while (base >= kTraceChunk) {
 #pragma unroll
             for (int j = 0; j < kTraceChunk; ++j) wc[j] = wn[j];
+            base -= kTraceChunk;
+            prefetch();
+            chunk(std::false_type{});
         }
     }
     __syncwarp();
@@ -515,15 +534,15 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     if (wbase < nframes) {
         const uint32_t rows = min(32u, nframes - wbase);
         const uint32_t total = rows * out_bytes;
-        const uint8_t* sb = reinterpret_cast<const uint8_t*>(my_smem);
         uint8_t* dst = out + (size_t)wbase * out_bytes;
-        uint32_t row = 0, col = lane;
-        while (col >= out_bytes) { col -= out_bytes; ++row; }
-        for (uint32_t i = lane; i < total; i += 32) {
-            dst[i] = sb[(size_t)row * stage_words * 4 + col];
-            col += 32;
-            while (col >= out_bytes) { col -= out_bytes; ++row; }
+        uint32_t done = 0;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const uint32_t n16 = total >> 4;
+            for (uint32_t i = lane; i < n16; i += 32)
+                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(tile)[i];
+            done = n16 << 4;
         }
+        for (uint32_t i = done + lane; i < total; i += 32) dst[i] = tile[i];
     }
 }
 
