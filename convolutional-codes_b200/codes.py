@@ -16,6 +16,7 @@ SOFT_F32 = 0
 HARD_U16 = 1
 SOFT_U8 = 2        # quantised soft: small integer branch metrics, uint8 [F][T][M]
 FORCE_GENERIC = 1
+PREFER_LANEGROUP = 2   # K = 8 .. 12: shuffle-exchange lane-group kernel instead of the register-tile kernel
 
 
 def left_align(octal: str, K: int) -> int:
@@ -78,6 +79,9 @@ K8_R12 = CodeParam(2, 8, 1024, (left_align("371", 8), left_align("247", 8)), "K8
 K9_R12 = CodeParam(2, 9, 1024, (left_align("561", 9), left_align("753", 9)), "K9 (561,753)")
 K10_R12 = CodeParam(2, 10, 1024, (left_align("1167", 10), left_align("1545", 10)), "K10 (1167,1545)")
 K11_R12 = CodeParam(2, 11, 1024, (left_align("2335", 11), left_align("3661", 11)), "K11 (2335,3661)")
+K12_R12 = CodeParam(2, 12, 1024, (left_align("4335", 12), left_align("5723", 12)), "K12 (4335,5723)")
+K13_R12 = CodeParam(2, 13, 1024, (left_align("10533", 13), left_align("17661", 13)), "K13 (10533,17661)")
+K14_R12 = CodeParam(2, 14, 1024, (left_align("21675", 14), left_align("27123", 14)), "K14 (21675,27123)")
 K15_R12 = CodeParam(2, 15, 1024, (left_align("46321", 15), left_align("51271", 15)), "K15 (46321,51271)")
 
 # noise scaling of the AWGN driver: sigma = 2^-1/2 * 10^(-EbN0_dB/20)  (AWGN-channel/main.c:153-161)

@@ -62,6 +62,13 @@ const char* regsw_name(const WideEntry* e);
 int regsw_run(const WideEntry* e, const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st);
 size_t regsw_bytes(const WideEntry* e, const LaunchGeom& g);
 
+// ---- register-tile kernels for K = 9 .. 15 (vdec_tile.cu): 2^(K-7) threads per frame, shared-memory transposes ----
+struct TileEntry;
+const TileEntry* tile_find(uint32_t K, uint32_t n, uint32_t metric, const uint8_t* labels);
+const char* tile_name(const TileEntry* e);
+int tile_run(const TileEntry* e, const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st);
+size_t tile_bytes(const TileEntry* e, const LaunchGeom& g);
+
 // ---- generic table-driven kernels (vdec_generic.cu) ----------------------------------------
 // One CTA per frame, path metrics in shared memory, labels from a device table; any K <= 15.
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
@@ -94,6 +101,7 @@ struct vdec {
     const vd::RegsEntry* regs;     // non-null => specialised kernel
     const vd::Regs2Entry* regs2;   // non-null => packed 16-bit kernel (takes precedence)
     const vd::WideEntry* regsw;    // non-null => lane-group register kernel (K = 8 .. 12)
+    const vd::TileEntry* tile;     // non-null => register-tile kernel (K = 9 .. 15)
     uint32_t* surv;                  // survivor scratch
     size_t surv_bytes;
     // host-buffer pipeline (vdec_decode_host)

@@ -54,7 +54,9 @@ enum vdec_parity {
 };
 
 enum vdec_flags {
-    VDEC_FORCE_GENERIC = 1u  /* never pick a code-specialised kernel (testing) */
+    VDEC_FORCE_GENERIC = 1u,    /* never pick a code-specialised kernel (testing) */
+    VDEC_PREFER_LANEGROUP = 2u  /* K = 8 .. 12: take the shuffle-exchange lane-group kernel instead of the
+                                   shared-memory register-tile kernel (A/B measurements, testing) */
 };
 
 /* Mirrors the fields of `struct code_param` the decoders read (common/include/code.h:9-19),

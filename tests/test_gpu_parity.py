@@ -63,13 +63,18 @@ SOFT_CASES = [  # (code getter, L, frames, sigma)
     ("k7r13", 300, 65, 0.6), ("k9", 128, 9, 0.5), ("k15", 40, 2, 0.5),
     # lane-group register kernels (2, 4, 8, 16 lanes per frame), ragged frame counts and lengths
     ("k8", 200, 67, 0.5), ("k9", 1024, 41, 0.45), ("k9", 3, 5, 0.5), ("k10", 150, 13, 0.5), ("k11", 97, 7, 0.5),
+    # register-tile kernels (4 .. 256 threads per frame): every window remainder T % 6, ragged frame counts
+    ("k9", 301, 131, 0.5), ("k10", 64, 70, 0.5), ("k11", 200, 37, 0.5), ("k12", 130, 19, 0.5), ("k12", 1, 9, 0.5),
+    ("k13", 77, 6, 0.5), ("k13", 1024, 5, 0.45), ("k14", 50, 5, 0.5), ("k15", 200, 3, 0.5), ("k15", 1, 2, 0.5),
+    ("k15", 1024, 2, 0.45),
 ]
 
 
 def _get(cc, key, L):
     table = {"cb0": cc.get_code(0), "cb1": cc.get_code(1), "cb2": cc.get_code(2), "cb3": cc.get_code(3),
              "cb5": cc.get_code(5), "k7r12": cc.codes.K7_R12, "k7r13": cc.codes.K7_R13, "k8": cc.codes.K8_R12, "k9": cc.codes.K9_R12,
-             "k10": cc.codes.K10_R12, "k11": cc.codes.K11_R12, "k15": cc.codes.K15_R12}
+             "k10": cc.codes.K10_R12, "k11": cc.codes.K11_R12, "k12": cc.codes.K12_R12, "k13": cc.codes.K13_R12,
+             "k14": cc.codes.K14_R12, "k15": cc.codes.K15_R12}
     return table[key].with_block_len(L)
 
 
@@ -82,9 +87,14 @@ def test_soft_vs_oracle(cc, orc, torch_cuda, key, L, F, sigma, parity):
     exp = orc.decode_soft(oc, met)
     out, name = _decode_soft(cc, torch_cuda, code, parity, met)
     assert np.array_equal(out, exp), f"{name}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
+    if parity == 1 and code.K >= 9:
+        assert name.startswith("tile_soft_f32"), name
     if code.K <= 11:   # the table-driven kernel must agree too
         out2, name2 = _decode_soft(cc, torch_cuda, code, parity, met, flags=cc.FORCE_GENERIC)
         assert name2.startswith("generic") and np.array_equal(out2, exp)
+    if parity == 1 and 8 <= code.K <= 11:   # and the shuffle-exchange lane-group kernel
+        out3, name3 = _decode_soft(cc, torch_cuda, code, parity, met, flags=cc.PREFER_LANEGROUP)
+        assert name3.startswith("regsw") and np.array_equal(out3, exp)
 
 
 HARD_CASES = [("cb0", 17000, 9, 0.05),      # too long for the shared-memory output tile: table-driven kernels
