@@ -16,6 +16,7 @@ SOFT_F32 = 0
 HARD_U16 = 1
 SOFT_U8 = 2        # quantised soft: small integer branch metrics, uint8 [F][T][M]
 FORCE_GENERIC = 1
+PREFER_32BIT = 4       # hard decisions: 32-bit register kernel instead of the packed 16-bit one
 PREFER_LANEGROUP = 2   # K = 8 .. 12: shuffle-exchange lane-group kernel instead of the register-tile kernel
 
 

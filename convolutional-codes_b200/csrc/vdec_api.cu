@@ -107,7 +107,7 @@ static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const
         else if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
         else rc = vd::generic_launch(g, h->cfg.metric, h->bfly_labels_dev, in, out, pm, p->sc.p[slot], st);
         if (rc != 0) return -1;
-        h->launches += (!h->tile && ((h->regs && !h->regs2) || h->regsw)) ? 1 : 2;   // packed path = transpose + decode; tile, table-driven = forward + traceback
+        h->launches += (!h->tile && (h->regs || h->regs2 || h->regsw)) ? 1 : 2;   // tile, table-driven = forward + traceback
         done += n;
     }
     return 0;
@@ -139,13 +139,16 @@ static void select_kernels(const vdec_config* cfg, const uint8_t* labels, const 
     // the register kernels stage a warp's output rows in shared memory: 16 B (32 B packed) per step and CTA
     const bool fits1 = T * 16 <= 200 * 1024, fits2 = T * 32 <= 200 * 1024;
     if (!fits1) return;
-    const bool small = T * (cfg->metric == VDEC_HARD_U16 ? cfg->symlen_out : (cfg->metric_max ? cfg->metric_max : 255)) < 0x8000u;
+    const bool small = T * (cfg->metric == VDEC_HARD_U16 ? cfg->symlen_out : (cfg->metric_max ? cfg->metric_max : 255)) < 0x4000u;
     if (cfg->metric == VDEC_SOFT_U8) {
         if (fits2 && small) *regs2 = vd::regs2_find(cfg->constr_len, cfg->symlen_out, 1, labels);
         return;
     }
-    // hard decisions: the 32-bit register kernel is currently the faster one (73 vs 60 Gbit/s at K=7,
-    // tools/bench_configs.py); the packed kernel serves labellings only it was instantiated for
+    // hard decisions: packed 16-bit kernel (2 issue slots per state update; 128 vs 75 Gbit/s at K=7, 627 vs 467
+    // at K=3, tools/bench_configs.py) when the metric range allows, else the 32-bit register kernel
+    if (!(cfg->flags & VDEC_PREFER_32BIT) && cfg->metric == VDEC_HARD_U16 && fits2 && small)
+        *regs2 = vd::regs2_find(cfg->constr_len, cfg->symlen_out, 0, labels);
+    if (*regs2) return;
     *regs = vd::regs_find(cfg->constr_len, cfg->symlen_out, cfg->metric, labels);
     if (!*regs && cfg->metric == VDEC_HARD_U16 && fits2 && small)
         *regs2 = vd::regs2_find(cfg->constr_len, cfg->symlen_out, 0, labels);

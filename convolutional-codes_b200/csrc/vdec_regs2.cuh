@@ -6,24 +6,33 @@
 // the reference's float decoder is exact integer arithmetic, so an integer kernel is bit-identical).
 //
 // Every 32-bit register holds the metric of the SAME state for TWO frames (low / high half), so one
-// instruction updates two frames:
-//     VIADD (32-bit add of packed halves; halves never carry: metrics < 2^15)
-//     VIMNMX.U16x2  — packed min that also returns one predicate per half (sm_90+ DPX), i.e. min AND
-//                     both decisions in a single issue slot
-//     2 predicated adds drop the decision bits into the survivor word
-// = 5 issue slots per TWO state updates, against 5 per ONE in the fp32 kernel.  Everything else
-// (in-place butterflies, rotation period K-1, compile-time labels, tie rule, lowest-index argmin,
+// instruction updates two frames.  Per butterfly (2 states x 2 frames = 4 state updates), 8 issue slots:
+//     2 x add            ce = pe + bm[even label]              (halves never carry: every metric < 2^15)
+//     2 x VIADDMNMX.U16x2  new = min(po + bm[odd label], ce)   (sm_90+ DPX: add and packed min in one slot)
+//     2 x IADD3          t  = ce - po + (0x7FFF7FFF - bm[odd]) = ce - co + 0x7FFF per half: bit 15 of each
+//                        half is set iff co < ce, i.e. the reference's strict '<' decision (tie -> even
+//                        predecessor, viterbi-decoder.c:122), with no borrow between the halves
+//     1 x PRMT           sign-replicates the four decision bytes of (t0, t1) into 0x00 / 0xFF bytes
+//     1 x LOP3           survivor word |= bytes & (0x01010101 << slot)
+// = 2 issue slots per state update and no predicate traffic, against ~4.4 in the fp32 kernel.  Measured
+// (tools/ubench/pipes.cu, profiles/r01l): VIADDMNMX, 3-input IADD3, PRMT and LOP3 all issue to the half-rate
+// ALU pipe, so the bound is 6 ALU slots = 12 clk per butterfly = 3 clk per state update (193 Gbit/s at K=7).  Everything
+// else (in-place butterflies, rotation period K-1, compile-time labels, tie rule, lowest-index argmin,
 // survivor scratch + prefetched traceback, staged output) is as in vdec_regs.cuh.
 //
-// Input is consumed from a transposed staging buffer written by pack_kernel (vdec_regs2.cu):
-//     tin[global warp][step][lane] = uint2 { frame 2*lane's step data, frame 2*lane+1's }
-// so each warp-step is one coalesced 256-byte read.
+// Input: every lane reads the rows of its two frames directly, one step (1 byte hard / 4 bytes quantised)
+// ahead of the ACS; a 32-byte sector serves 32 / 8 consecutive steps of a row and stays in L1 meanwhile
+// (128 threads x 2 rows x 4 CTAs x 32 B = 32 KB per SM), so no transposing pre-pass is needed.
 //
-// Range: unreachable = 0x8000, real metrics must stay below it: T * max_branch_metric < 0x8000 is
-// checked on the host (the 32-bit kernels take over otherwise).  Below that bound the reference's
-// clamp at 0xFF00 (viterbi-decoder.c:127-130) can never trigger, so decisions, final state and
-// path_metric are identical; states still unreachable never win a compare against a real metric and
-// are never visited by the traceback.
+// Range: unreachable = 0x4000 and every metric must stay below 0x8000 (so that differences of two
+// metrics fit 16 bits signed): T * max_branch_metric < 0x4000 is checked on the host (the 32-bit kernels
+// take over otherwise).  Below that bound the reference's clamp at 0xFF00 (viterbi-decoder.c:127-130) can
+// never trigger on a reachable state, so decisions along every survivor the traceback can visit, the
+// final state and path_metric are identical; states still unreachable never win a compare against a real
+// metric and are never visited by the traceback.
+//
+// Survivor word layout: butterfly m = j mod S/2 of new state j, h = top bit of j, frame fr in {0,1}:
+// word m / 8, bit 8 * (2h + fr) + m % 8.
 #pragma once
 #include <type_traits>
 #include <utility>
@@ -32,7 +41,9 @@
 
 namespace vd {
 
-constexpr uint32_t kBig2 = 0x80008000u;
+constexpr uint32_t kBig2 = 0x40004000u;       // unreachable, both halves
+constexpr uint32_t kBias2 = 0x7FFF7FFFu;
+constexpr uint32_t kRegs2Limit = 0x4000u;     // T * max branch metric must stay below this
 
 enum { kModeHard = 0, kModeQuant = 1 };
 
@@ -53,41 +64,32 @@ __device__ __forceinline__ void packed_bm(uint2 x, uint32_t (&bm)[M]) {
     }
 }
 
-// packed min of two frames' candidates plus both decisions: min.u16x2 + the two setp.eq on the halves
-// are what __vibmin_u16x2 expands to and what ptxas fuses into ONE VIMNMX.U16x2 with two predicate
-// outputs; pred = (min == even) = (even <= odd), so the decision "odd strictly smaller" (tie -> even
-// predecessor, viterbi-decoder.c:122) is its negation and ORs the frame's bit into the survivor word.
-__device__ __forceinline__ uint32_t acs2(uint32_t ce, uint32_t co, uint32_t& dw, uint32_t bit_lo, uint32_t bit_hi) {
-    uint32_t mn;
-    asm("{\n\t.reg .pred pu, pv;\n\t.reg .u16 rs0, rs1, rs2, rs3;\n\t"
-        "min.u16x2 %0, %2, %3;\n\t"
-        "mov.b32 {rs0, rs1}, %0;\n\t"
-        "mov.b32 {rs2, rs3}, %2;\n\t"
-        "setp.eq.u16 pv, rs0, rs2;\n\t"
-        "setp.eq.u16 pu, rs1, rs3;\n\t"
-        "@!pv or.b32 %1, %1, %4;\n\t"
-        "@!pu or.b32 %1, %1, %5;\n\t}"
-        : "=r"(mn), "+r"(dw) : "r"(ce), "r"(co), "r"(bit_lo), "r"(bit_hi));
-    return mn;
-}
-
-template <int S> struct Surv2 { static constexpr int NW = (S + 15) / 16; };   // 16 states x 2 frames per word
+template <int S> struct Surv2 { static constexpr int NW = (S + 15) / 16; };   // 8 butterflies x 2 states x 2 frames per word
 
 template <class CD, int PH>
 __device__ __forceinline__ void acs_step2(uint32_t (&r)[CD::S], const uint32_t (&bm)[CD::M], uint32_t (&dw)[Surv2<CD::S>::NW]) {
-    constexpr int B = CD::B, S = CD::S, PB = PH % B;
+    constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M;
+    uint32_t kb[M];
+#pragma unroll
+    for (int e = 0; e < M; ++e) kb[e] = kBias2 - bm[e];
 #pragma unroll
     for (int w = 0; w < Surv2<S>::NW; ++w) dw[w] = 0;
-#pragma unroll
-    for (int a = 0; a < S; ++a) {
-        if ((a >> PB) & 1) continue;
-        const int b = a | (1 << PB);
-        const uint32_t u = rotr_bits(a, PH, B), v = u + 1;
-        const uint32_t j0 = u >> 1, j1 = j0 + S / 2;
-        const uint32_t pe = r[a], po = r[b];
-        r[a] = acs2(pe + bm[CD::label(u, 0)], po + bm[CD::label(v, 0)], dw[j0 >> 4], 1u << (j0 & 15), 1u << (16 + (j0 & 15)));
-        r[b] = acs2(pe + bm[CD::label(u, 1)], po + bm[CD::label(v, 1)], dw[j1 >> 4], 1u << (j1 & 15), 1u << (16 + (j1 & 15)));
-    }
+    static_for<0, S>([&](auto ac) {
+        constexpr int a = decltype(ac)::value;
+        if constexpr (((a >> PB) & 1) == 0) {
+            constexpr int b = a | (1 << PB);
+            constexpr uint32_t u = rotr_bits(a, PH, B), v = u + 1, m = u >> 1;     // new states m (input 0) and m + S/2 (input 1)
+            const uint32_t pe = r[a], po = r[b];
+            const uint32_t ce0 = pe + bm[CD::label(u, 0)], ce1 = pe + bm[CD::label(u, 1)];
+            const uint32_t t0 = ce0 - po + kb[CD::label(v, 0)];
+            const uint32_t t1 = ce1 - po + kb[CD::label(v, 1)];
+            r[a] = __viaddmin_u16x2(po, bm[CD::label(v, 0)], ce0);
+            r[b] = __viaddmin_u16x2(po, bm[CD::label(v, 1)], ce1);
+            uint32_t p;
+            asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(p) : "r"(t0), "r"(t1));   // bytes: (A,m) (B,m) (A,m+S/2) (B,m+S/2), 0x00 / 0xFF
+            dw[m >> 3] |= p & (0x01010101u << (m & 7));
+        }
+    });
 }
 
 template <int NW> struct SurvVec;
@@ -102,33 +104,37 @@ __device__ __forceinline__ uint32_t surv_word(const typename SurvVec<NW>::type& 
     else return (idx & 2) ? ((idx & 1) ? v.w : v.z) : ((idx & 1) ? v.y : v.x);
 }
 
-constexpr int kTrace2Chunk = 8;
+constexpr int kTrace2Chunk = 16;
 
 template <class CD, int MODE>
 __global__ void __launch_bounds__(kRegsThreads, 4)
-vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
-                 uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t stage_words,
-                 uint32_t init_all_from) {
+vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
+                 uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t tile_bytes,
+                 uint32_t stride_steps, uint32_t init_all_from) {
     constexpr int S = CD::S, B = CD::B, M = CD::M, NW = Surv2<S>::NW;
     using SV = typename SurvVec<NW>::type;
-    extern __shared__ __align__(16) unsigned char s_raw[];      // output staging: [warp][64 rows][stage_words]
+    extern __shared__ __align__(16) unsigned char s_raw[];      // output staging: [warp][64 rows][out_bytes], tile_bytes per warp
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gt = blockIdx.x * kRegsThreads + tid;        // thread <-> frames 2*gt, 2*gt+1
     const uint32_t gw = gt >> 5;
     const uint32_t fA = 2 * gt, fB = fA + 1;
     const bool liveA = fA < nframes, liveB = fB < nframes;
-    const uint2* src = tin + (size_t)gw * T * 32 + lane;
+    // rows of the two frames; a dead frame shadows the last live one and stores nothing
+    using Elem = std::conditional_t<MODE == kModeHard, uint8_t, uint32_t>;      // one step: 1 symbol byte / 4 metric bytes
+    const Elem* rowA = static_cast<const Elem*>(in) + (size_t)min(fA, nframes - 1) * stride_steps;
+    const Elem* rowB = static_cast<const Elem*>(in) + (size_t)min(fB, nframes - 1) * stride_steps;
+    auto fetch = [&](uint32_t t) { return make_uint2((uint32_t)__ldg(rowA + t), (uint32_t)__ldg(rowB + t)); };
     SV* sv = reinterpret_cast<SV*>(surv) + (size_t)gw * T * 32 + lane;
 
     uint32_t r[S];
     r[0] = 0;                                                   // :225
-    const uint32_t rest = (fA >= init_all_from ? 0u : 0x8000u) | (fB >= init_all_from ? 0u : 0x80000000u);
+    const uint32_t rest = (fA >= init_all_from ? 0u : (kBig2 & 0xFFFFu)) | (fB >= init_all_from ? 0u : (kBig2 & 0xFFFF0000u));
 #pragma unroll
     for (int s = 1; s < S; ++s) r[s] = rest;                    // unreachable (:226-228) unless the start is unknown
 
     uint32_t dw[NW], bm[M];
-    uint2 xn = __ldg(src);
+    uint2 xn = fetch(0);
     auto store_dw = [&](uint32_t t) {
         SV v;
         if constexpr (NW == 1) v = dw[0];
@@ -142,7 +148,7 @@ vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32
         static_for<0, B>([&](auto phc) {
             constexpr int PH = decltype(phc)::value;
             const uint2 x = xn;
-            xn = __ldg(src + (size_t)min(t + PH + 1, T - 1) * 32);           // one step of lookahead, coalesced
+            xn = fetch(min(t + PH + 1, T - 1));                                // one step of lookahead
             packed_bm<M, MODE>(x, bm);
             acs_step2<CD, PH>(r, bm, dw);
             store_dw(t + PH);
@@ -153,7 +159,7 @@ vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32
         constexpr int PH = decltype(phc)::value;
         if (PH < (int)rem) {
             const uint2 x = xn;
-            xn = __ldg(src + (size_t)min(t + PH + 1, T - 1) * 32);
+            xn = fetch(min(t + PH + 1, T - 1));
             packed_bm<M, MODE>(x, bm);
             acs_step2<CD, PH>(r, bm, dw);
             store_dw(t + PH);
@@ -179,39 +185,57 @@ vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32
         if (liveB) path_metric[fB] = (int32_t)bestB;
     }
 
-    // traceback of both frames (:84-93); survivor vectors fetched a chunk ahead
-    uint32_t* stage = reinterpret_cast<uint32_t*>(s_raw) + ((size_t)warp * 64 + 2 * lane) * stage_words;
+    // traceback of both frames (:84-93); survivor vectors fetched a chunk ahead.  As in vdec_regs.cuh the
+    // state of each frame is an unmasked shift register (cur = h & (S-1)) whose bits B-1.. are the decoded
+    // bits, emitted 16 at a time into the warp's tile (64 rows at their final out_bytes pitch).
+    unsigned char* tile = s_raw + (size_t)warp * tile_bytes;
     if (liveA) {
+        unsigned char* rowA = tile + (size_t)(2 * lane) * out_bytes;
+        unsigned char* rowB = rowA + out_bytes;
         SV wc[kTrace2Chunk], wn[kTrace2Chunk];
         int base = ((int)T - 1) & ~(kTrace2Chunk - 1);
 #pragma unroll
         for (int j = 0; j < kTrace2Chunk; ++j)
             if (base + j < (int)T) wc[j] = __ldcg(sv + (size_t)(base + j) * 32);
-        uint32_t accA = 0, accB = 0;
-        for (; base >= 0; base -= kTrace2Chunk) {
+        uint32_t hA = curA, hB = curB;
+        auto pick = [&](const SV& v, uint32_t h, uint32_t fr) -> uint32_t {
+            const uint32_t cur = h & (S - 1), m = cur & (S / 2 - 1);
+            const uint32_t word = surv_word<NW>(v, m >> 3);
+            return (word >> (8 * (2 * (cur >> (B - 1)) + fr) + (m & 7))) & 1u;
+        };
+        auto chunk = [&](auto guard) {
+            constexpr bool GUARD = decltype(guard)::value;
+#pragma unroll
+            for (int j = kTrace2Chunk - 1; j >= 0; --j) {
+                const int tt = base + j;
+                if (GUARD && tt >= (int)T) continue;
+                if ((j & 15) == 0) {
+                    const uint32_t ra = __brev(hA >> (B - 1)), rb = __brev(hB >> (B - 1));
+                    rowA[tt >> 3] = (unsigned char)(ra >> 24);
+                    rowB[tt >> 3] = (unsigned char)(rb >> 24);
+                    if (!GUARD || tt + 8 < (int)T) {
+                        rowA[(tt >> 3) + 1] = (unsigned char)(ra >> 16);
+                        rowB[(tt >> 3) + 1] = (unsigned char)(rb >> 16);
+                    }
+                }
+                hA = (hA << 1) | pick(wc[j], hA, 0);
+                hB = (hB << 1) | pick(wc[j], hB, 1);
+            }
+        };
+        auto prefetch = [&]() {
             if (base >= kTrace2Chunk) {
 #pragma unroll
                 for (int j = 0; j < kTrace2Chunk; ++j) wn[j] = __ldcg(sv + (size_t)(base - kTrace2Chunk + j) * 32);
             }
-#pragma unroll
-            for (int j = kTrace2Chunk - 1; j >= 0; --j) {
-                const int tt = base + j;
-                if (tt < (int)T) {
-                    const uint32_t dA = (surv_word<NW>(wc[j], curA >> 4) >> (curA & 15)) & 1u;
-                    const uint32_t dB = (surv_word<NW>(wc[j], curB >> 4) >> (16 + (curB & 15))) & 1u;
-                    accA |= (curA >> (B - 1)) << (31 - (tt & 31));
-                    accB |= (curB >> (B - 1)) << (31 - (tt & 31));
-                    curA = ((curA << 1) & (S - 1)) | dA;
-                    curB = ((curB << 1) & (S - 1)) | dB;
-                    if ((tt & 31) == 0) {
-                        stage[tt >> 5] = __byte_perm(accA, 0, 0x0123);
-                        stage[stage_words + (tt >> 5)] = __byte_perm(accB, 0, 0x0123);
-                        accA = 0; accB = 0;
-                    }
-                }
-            }
+        };
+        prefetch();
+        chunk(std::true_type{});
+        while (base >= kTrace2Chunk) {
 #pragma unroll
             for (int j = 0; j < kTrace2Chunk; ++j) wc[j] = wn[j];
+            base -= kTrace2Chunk;
+            prefetch();
+            chunk(std::false_type{});
         }
     }
     __syncwarp();
@@ -221,42 +245,15 @@ vit_regs2_kernel(const uint2* __restrict__ tin, uint8_t* __restrict__ out, int32
     if (wbase < nframes) {
         const uint32_t rows = min(64u, nframes - wbase);
         const uint32_t total = rows * out_bytes;
-        const uint8_t* sb = s_raw + (size_t)warp * 64 * stage_words * 4;
         uint8_t* dst = out + (size_t)wbase * out_bytes;
-        uint32_t row = 0, col = lane;
-        while (col >= out_bytes) { col -= out_bytes; ++row; }
-        for (uint32_t i = lane; i < total; i += 32) {
-            dst[i] = sb[(size_t)row * stage_words * 4 + col];
-            col += 32;
-            while (col >= out_bytes) { col -= out_bytes; ++row; }
+        uint32_t done = 0;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const uint32_t n16 = total >> 4;
+            for (uint32_t i = lane; i < n16; i += 32)
+                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(tile)[i];
+            done = n16 << 4;
         }
-    }
-}
-
-// ---- transposition of the caller's rows into the kernel's coalesced staging layout ---------------
-// hard: in = uint8 [F][T] (one symbol per step); quant: in = uint8 [F][T][4]
-// One CTA = one warp-group of 64 frames x kPackSteps steps: rows are read along t (coalesced), parked in
-// shared memory, and written out so that the 32 lanes' uint2 of one step form one 256-byte line.
-constexpr int kPackSteps = 64;
-template <int MODE>
-__global__ void __launch_bounds__(256)
-pack2_kernel(const uint8_t* __restrict__ in, uint2* __restrict__ tin, uint32_t nframes, uint32_t T, uint32_t stride) {
-    __shared__ uint32_t tile[64][kPackSteps + 1];
-    const uint32_t gw = blockIdx.y, t0 = blockIdx.x * kPackSteps, tid = threadIdx.x;
-    const uint32_t steps = min((uint32_t)kPackSteps, T - t0);
-    for (uint32_t i = tid; i < 64 * kPackSteps; i += 256) {
-        const uint32_t row = i / kPackSteps, c = i % kPackSteps;
-        uint32_t f = gw * 64 + row;
-        if (f >= nframes) f = nframes - 1;                       // an odd tail shadows the last frame
-        if (c < steps) {
-            if constexpr (MODE == kModeHard) tile[row][c] = in[(size_t)f * stride + t0 + c];
-            else tile[row][c] = __ldg(reinterpret_cast<const uint32_t*>(in) + (size_t)f * stride + t0 + c);
-        }
-    }
-    __syncthreads();
-    for (uint32_t i = tid; i < 32 * steps; i += 256) {
-        const uint32_t c = i >> 5, lane = i & 31;
-        tin[((size_t)gw * T + t0 + c) * 32 + lane] = make_uint2(tile[2 * lane][c], tile[2 * lane + 1][c]);
+        for (uint32_t i = done + lane; i < total; i += 32) dst[i] = tile[i];
     }
 }
 
@@ -272,24 +269,19 @@ const Regs2Entry* regs2_find(uint32_t K, uint32_t n, uint32_t mode, const uint8_
 template <class CD>
 size_t regs2_scratch_bytes(const LaunchGeom& g) {
     const size_t warps = ((size_t)(g.nframes + 1) / 2 + 31) / 32;
-    return warps * g.T * 32 * (sizeof(uint2) + Surv2<CD::S>::NW * sizeof(uint32_t));    // staging + survivors
+    return warps * g.T * 32 * Surv2<CD::S>::NW * sizeof(uint32_t);                       // survivors
 }
 
 template <class CD, int MODE>
 int regs2_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* scratch, cudaStream_t st) {
-    const size_t npairs = ((size_t)g.nframes + 1) / 2, warps = (npairs + 31) / 32;
-    uint2* tin = reinterpret_cast<uint2*>(scratch);
-    uint32_t* surv = reinterpret_cast<uint32_t*>(tin + warps * g.T * 32);
-    pack2_kernel<MODE><<<dim3((g.T + kPackSteps - 1) / kPackSteps, (unsigned)warps), 256, 0, st>>>(
-        static_cast<const uint8_t*>(in), tin, g.nframes, g.T, g.stride_steps);
-    VDEC_CUDA(cudaGetLastError());
-    uint32_t stage_words = (g.out_bytes + 3) / 4;
-    if ((stage_words & 1) == 0) ++stage_words;
-    const size_t smem = (size_t)(kRegsThreads / 32) * 64 * stage_words * 4;
+    const size_t npairs = ((size_t)g.nframes + 1) / 2;
+    const uint32_t tile_bytes = (64 * g.out_bytes + 15) & ~15u;
+    const size_t smem = (size_t)(kRegsThreads / 32) * tile_bytes;
     auto kern = vit_regs2_kernel<CD, MODE>;
     if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (uint32_t)((npairs + kRegsThreads - 1) / kRegsThreads);
-    kern<<<blocks, kRegsThreads, smem, st>>>(tin, out, path_metric, surv, g.nframes, g.T, g.out_bytes, stage_words, g.init_all_from);
+    kern<<<blocks, kRegsThreads, smem, st>>>(in, out, path_metric, scratch, g.nframes, g.T, g.out_bytes, tile_bytes,
+                                              g.stride_steps, g.init_all_from);
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }

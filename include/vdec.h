@@ -55,8 +55,10 @@ enum vdec_parity {
 
 enum vdec_flags {
     VDEC_FORCE_GENERIC = 1u,    /* never pick a code-specialised kernel (testing) */
-    VDEC_PREFER_LANEGROUP = 2u  /* K = 8 .. 12: take the shuffle-exchange lane-group kernel instead of the
+    VDEC_PREFER_LANEGROUP = 2u, /* K = 8 .. 12: take the shuffle-exchange lane-group kernel instead of the
                                    shared-memory register-tile kernel (A/B measurements, testing) */
+    VDEC_PREFER_32BIT = 4u      /* hard decisions: take the 32-bit register kernel instead of the packed 16-bit one
+                                   (A/B measurements, testing) */
 };
 
 /* Mirrors the fields of `struct code_param` the decoders read (common/include/code.h:9-19),
@@ -73,7 +75,7 @@ struct vdec_config {
     uint32_t max_frames;               /* frames per kernel launch; 0 = default */
     uint64_t polynomials[VDEC_MAX_POLY];
     uint32_t metric_max;               /* VDEC_SOFT_U8: largest branch metric the caller will pass (0 = 255);
-                                          T * metric_max < 32768 selects the packed 16-bit kernels */
+                                          T * metric_max < 16384 selects the packed 16-bit kernels */
     uint32_t reserved;
 };
 

@@ -43,7 +43,8 @@ def test_kernel_selection(cc):
     assert cc.config_kernel_name(cc.codes.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K15")
     assert cc.config_kernel_name(cc.codes.K15_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("generic_soft_f32<K15")
     # hard decisions: 32-bit register kernel; packed 16-bit kernel only for labellings the former lacks
-    assert cc.config_kernel_name(cc.get_code(0), cc.HARD_U16).startswith("regs_hard_u16<codebook0")
+    assert cc.config_kernel_name(cc.get_code(0), cc.HARD_U16).startswith("regs2_hard_u16x2<codebook0")
+    assert cc.config_kernel_name(cc.get_code(0), cc.HARD_U16, cc.PARITY_REF, cc.PREFER_32BIT).startswith("regs_hard_u16<codebook0")
     assert cc.config_kernel_name(cc.codes.K7_R13, cc.HARD_U16).startswith("regs2_hard_u16x2<K7 (133,171,165) ref")
     # frames too long for the shared-memory output tile go to the table-driven kernels
     assert cc.config_kernel_name(cc.get_code(0).with_block_len(20000), cc.HARD_U16).startswith("generic_hard_u16")

@@ -27,10 +27,11 @@ def main():
         ("C1 hard K3 cb0 L40", cc.get_code(0), cc.HARD_U16, cc.PARITY_REF, (1 << 20) // q, 0),
         ("C1' soft K3 cb0 L40", cc.get_code(0), cc.SOFT_F32, cc.PARITY_REF, (1 << 20) // q, 0),
         ("cb3 soft K6 L40", cc.get_code(3), cc.SOFT_F32, cc.PARITY_REF, (1 << 20) // q, 0),
-        ("C2 soft K7 r1/2 L1024 ref", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, (1 << 19) // q, 0),
-        ("C2 soft K7 r1/2 L1024 linear", C.K7_R12, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 19) // q, 0),
-        ("C2h hard K7 r1/2 L1024", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, (1 << 19) // q, 0),
-        ("f3 quant K7 r1/2 L1024 (u8 metrics <= 7)", C.K7_R12, cc.SOFT_U8, cc.PARITY_LINEAR, (1 << 19) // q, 0),
+        ("C2 soft K7 r1/2 L1024 ref", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 1000000 // q, 0),
+        ("C2 soft K7 r1/2 L1024 linear", C.K7_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 1000000 // q, 0),
+        ("C2h hard K7 r1/2 L1024", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, 0),
+        ("C2h hard K7 r1/2 L1024 (32-bit kernel)", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, cc.PREFER_32BIT),
+        ("f3 quant K7 r1/2 L1024 (u8 metrics <= 7)", C.K7_R12, cc.SOFT_U8, cc.PARITY_LINEAR, 1000000 // q, 0),
         ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, (1 << 18) // q, 0),
         ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 18) // q, 0),
         ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),

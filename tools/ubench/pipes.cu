@@ -25,13 +25,15 @@ enum { OP_FADD, OP_FADD2, OP_FMNMX, OP_IADD, OP_IMAD, OP_SHF, OP_LOP, OP_SETPSEL
        MIX_F2_MNMX,   // FADD2 : FMNMX 1:1  -> does FADD2 take one issue slot or two?
        MIX_F2_MNMX2,  // FADD2 : FMNMX 1:2
        MIX_F2_FADD,   // FADD2 : FADD 1:1
+       OP_VIADDMNMX, OP_PRMT, OP_IADD3_3, MIX_VAM_IADD3, MIX_VAM_LOP, MIX_VAM_IMAD, MIX_PACKED,   // packed 16-bit recipe (vdec_regs2.cuh)
        NOPS };
 static const char* names[NOPS] = {"FADD", "FADD2", "FMNMX", "IADD3", "IMAD", "SHF", "LOP3", "FSETP+SELP",
   "FADD+FMNMX", "FADD+IADD3", "FADD+IMAD", "FMNMX+IADD3",
   "ACS_A 2FADD+FMNMX+IADD+SHF", "ACS_B 2FADD+FSETP+SELP+@pOR", "ACS_C FADD2+2(FMNMX+IADD+SHF)",
-  "ACS_D FADD2+2(FMNMX+FADDdiff+SHF)", "ACS_E FADD2+2(FMNMX+IMADdiff+SHF)", "ACS_F 2FADD+FMNMX+FADDdiff+SHF", "FADD2+FMNMX 1:1", "FADD2+2FMNMX", "FADD2+FADD 1:1"};
+  "ACS_D FADD2+2(FMNMX+FADDdiff+SHF)", "ACS_E FADD2+2(FMNMX+IMADdiff+SHF)", "ACS_F 2FADD+FMNMX+FADDdiff+SHF", "FADD2+FMNMX 1:1", "FADD2+2FMNMX", "FADD2+FADD 1:1",
+  "VIADDMNMX.U16x2", "PRMT", "IADD3 (3-input)", "VIADDMNMX+IADD3", "VIADDMNMX+LOP3", "VIADDMNMX+IMAD", "PACKED 2ADD+2VIADDMNMX+2IADD3+PRMT+LOP3"};
 // instructions per chain-iteration for each op
-static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5, 2, 3, 2};
+static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5, 2, 3, 2, 2, 2, 2, 2, 2, 2, 8};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, long long* cyc) {
@@ -106,6 +108,24 @@ __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, lon
       if (OP == MIX_F2_FADD) {
         asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(c2));
         asm volatile("add.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i]));
+      }
+      if (OP == OP_VIADDMNMX) { asm volatile("{.reg .b32 t; add.u16x2 t, %0, %1; min.u16x2 %0, t, %2;}" : "+r"(u[i]) : "r"(v[i]), "r"(cu)); asm volatile("{.reg .b32 t; add.u16x2 t, %0, %1; min.u16x2 %0, t, %2;}" : "+r"(v[i]) : "r"(u[i]), "r"(cu)); }
+      if (OP == OP_PRMT) { asm volatile("prmt.b32 %0, %0, %1, 0xFDB9;" : "+r"(u[i]) : "r"(v[i])); asm volatile("prmt.b32 %0, %0, %1, 0xFDB9;" : "+r"(v[i]) : "r"(u[i])); }
+      if (OP == OP_IADD3_3) { asm volatile("{.reg .b32 t; sub.s32 t, %0, %1; add.s32 %0, t, %2;}" : "+r"(u[i]) : "r"(v[i]), "r"(cu)); asm volatile("{.reg .b32 t; sub.s32 t, %0, %1; add.s32 %0, t, %2;}" : "+r"(v[i]) : "r"(u[i]), "r"(cu)); }
+      if (OP == MIX_VAM_IADD3) { asm volatile("{.reg .b32 t; add.u16x2 t, %0, %1; min.u16x2 %0, t, %2;}" : "+r"(u[i]) : "r"(v[i]), "r"(cu)); asm volatile("{.reg .b32 t; sub.s32 t, %0, %1; add.s32 %0, t, %2;}" : "+r"(v[i]) : "r"(u[i]), "r"(cu)); }
+      if (OP == MIX_VAM_LOP) { asm volatile("{.reg .b32 t; add.u16x2 t, %0, %1; min.u16x2 %0, t, %2;}" : "+r"(u[i]) : "r"(v[i]), "r"(cu)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(v[i]) : "r"(u[i]), "r"(cu)); }
+      if (OP == MIX_VAM_IMAD) { asm volatile("{.reg .b32 t; add.u16x2 t, %0, %1; min.u16x2 %0, t, %2;}" : "+r"(u[i]) : "r"(v[i]), "r"(cu)); asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(v[i]) : "r"(u[i])); }
+      if (OP == MIX_PACKED) {
+        uint32_t ce0, ce1, t0, t1, p, n0, n1;
+        asm volatile("add.s32 %0, %1, %2;" : "=r"(ce0) : "r"(u[i]), "r"(cu));
+        asm volatile("add.s32 %0, %1, %2;" : "=r"(ce1) : "r"(u[i]), "r"(cu + 1));
+        asm volatile("{.reg .b32 t; sub.s32 t, %1, %2; add.s32 %0, t, %3;}" : "=r"(t0) : "r"(ce0), "r"(v[i]), "r"(cu));
+        asm volatile("{.reg .b32 t; sub.s32 t, %1, %2; add.s32 %0, t, %3;}" : "=r"(t1) : "r"(ce1), "r"(v[i]), "r"(cu));
+        asm volatile("{.reg .b32 t; add.u16x2 t, %1, %2; min.u16x2 %0, t, %3;}" : "=r"(n0) : "r"(v[i]), "r"(cu), "r"(ce0));
+        asm volatile("{.reg .b32 t; add.u16x2 t, %1, %2; min.u16x2 %0, t, %3;}" : "=r"(n1) : "r"(v[i]), "r"(cu + 1), "r"(ce1));
+        asm volatile("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(p) : "r"(t0), "r"(t1));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(((uint32_t*)&d[i])[0]) : "r"(p), "r"(cu));
+        u[i] = n0; v[i] = n1;
       }
       if (OP == MIX_ACS_F) {
         float c0, c1, e0;
