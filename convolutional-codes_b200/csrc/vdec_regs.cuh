@@ -383,7 +383,7 @@ template <int M, int B> struct FeederOf<HardU16, M, B> { using type = HardDirect
 #define VDEC_TRACE_CHUNK 16
 #endif
 constexpr int kTraceChunk = VDEC_TRACE_CHUNK;     // survivor words prefetched per traceback chunk
-static_assert(kTraceChunk % 16 == 0, "traceback emits 16 output bits per 16 steps");
+static_assert(kTraceChunk == 16, "traceback emits 16 output bits per 16-step chunk");
 
 template <class CD, class MP>
 __global__ void __launch_bounds__(kRegsThreads, (MP::kPacked ? CD::kMinBlocks : 4))
@@ -480,51 +480,81 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     // (coalesced: 32 lanes x NW words).  The state is kept as an unmasked shift register `h`
     // (cur = h & (S-1)): the decoded bit of step tt is the decision taken B-1 steps later on the way
     // back, so bit B-1+i of h at step tt is the decoded bit of step tt+i and 16 output bits fall out
-    // of h every 16 steps without any per-step accumulation.  Dependent chain per step: one variable
-    // shift and one 3-input logic op; the survivor-word select hangs on bit B-1 of cur, known B-1
-    // steps earlier.  Rows are staged at their final out_bytes pitch, so the warp's tile is the
-    // byte image of its 32 contiguous output rows.
+    // of h every 16 steps without any per-step accumulation.  Rows are staged at their final out_bytes
+    // pitch, so the warp's tile is the byte image of its 32 contiguous output rows.
     unsigned char* tile = my_smem;
     if (live) {
+        // Two register sets (A, B) of 16 steps each: the words of chunk c-1 are requested before chunk c is
+        // walked, and an L2 prefetch runs three chunks further ahead (one 128-byte line per lane), so the walk
+        // never waits for HBM.  For S = 64 the word of a step (x: states 0..31, y: 32..63) is chosen by bit 5 of
+        // cur, i.e. by the decision taken 6 steps earlier on the way back: the select is done then (`sa`, `sb`)
+        // and the dependent chain of a step is one variable shift and one 3-input logic op.
         const SW* svw = reinterpret_cast<const SW*>(sv);
         unsigned char* srow = tile + (size_t)lane * out_bytes;
-        SW wc[kTraceChunk], wn[kTraceChunk];
+        SW wa[kTraceChunk], wb[kTraceChunk];
+        [[maybe_unused]] uint32_t sa[kTraceChunk], sb[kTraceChunk];
         int base = ((int)T - 1) & ~(kTraceChunk - 1);
+        const int jmax = ((int)T - 1) & (kTraceChunk - 1);
+        uint32_t h = cur;
+        auto l2_prefetch = [&](int cb) {          // chunk starting at step cb: 16 * NW lines, one per lane
+            if (cb >= 0 && lane < 16u * NW)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(svw) - (size_t)lane * NW * 4 +
+                                                               (size_t)cb * 128 * NW + (size_t)lane * 128));
+        };
+        auto load = [&](SW (&w)[kTraceChunk], int cb) {
+            if (cb >= 0) {
+#pragma unroll
+                for (int j = 0; j < kTraceChunk; ++j) w[j] = __ldcg(svw + (size_t)(cb + j) * 32);
+            }
+        };
 #pragma unroll
         for (int j = 0; j < kTraceChunk; ++j)
-            if (base + j < (int)T) wc[j] = __ldcg(svw + (size_t)(base + j) * 32);
-        uint32_t h = cur;
-        auto chunk = [&](auto guard) {
+            if (j <= jmax) wa[j] = __ldcg(svw + (size_t)(base + j) * 32);
+        load(wb, base - kTraceChunk);
+        l2_prefetch(base - 2 * kTraceChunk);
+        l2_prefetch(base - 3 * kTraceChunk);
+        if constexpr (NW == 2) {                  // the last 6 steps take their word-select bit from the final state itself
+#pragma unroll
+            for (int j = 0; j < kTraceChunk; ++j) {
+                const int ia = jmax - j, ib = jmax + kTraceChunk - j;       // steps back from T-1
+                if (ia >= 0 && ia <= 5) sa[j] = ((cur >> (5 - ia)) & 1u) ? wa[j].y : wa[j].x;
+                if (ib <= 5) sb[j] = ((cur >> (5 - ib)) & 1u) ? wb[j].y : wb[j].x;
+            }
+        }
+        auto walk = [&](SW (&cw)[kTraceChunk], uint32_t (&cs)[kTraceChunk], SW (&nw)[kTraceChunk], uint32_t (&ns)[kTraceChunk], auto guard) {
             constexpr bool GUARD = decltype(guard)::value;      // first chunk only: steps >= T do not exist
 #pragma unroll
             for (int j = kTraceChunk - 1; j >= 0; --j) {
                 const int tt = base + j;
-                if (GUARD && tt >= (int)T) continue;
+                if (GUARD && j > jmax) continue;
                 if ((j & 15) == 0) {                             // bits tt .. tt+15 -> bytes tt/8, tt/8+1, MSB-first (:88)
                     const uint32_t rv = __brev(h >> (B - 1));
                     srow[tt >> 3] = (unsigned char)(rv >> 24);
                     if (!GUARD || tt + 8 < (int)T) srow[(tt >> 3) + 1] = (unsigned char)(rv >> 16);
                 }
                 uint32_t word;
-                if constexpr (NW == 1) word = wc[j];
-                else word = (h & 32u) ? wc[j].y : wc[j].x;
-                h = (h << 1) | ((word >> (h & (S - 1) & 31u)) & 1u);   // predecessor (:86)
+                if constexpr (NW == 1) word = cw[j];
+                else word = cs[j];
+                const uint32_t d = (word >> (h & (S - 1) & 31u)) & 1u;
+                h = (h << 1) | d;                                               // predecessor (:86)
+                if constexpr (NW == 2) {                         // d is bit 5 of cur six steps further back
+                    if (j >= 6) cs[j - 6] = d ? cw[j - 6].y : cw[j - 6].x;
+                    else ns[j + kTraceChunk - 6] = d ? nw[j + kTraceChunk - 6].y : nw[j + kTraceChunk - 6].x;
+                }
             }
         };
-        auto prefetch = [&]() {
-            if (base >= kTraceChunk) {
-#pragma unroll
-                for (int j = 0; j < kTraceChunk; ++j) wn[j] = __ldcg(svw + (size_t)(base - kTraceChunk + j) * 32);
-            }
-        };
-        prefetch();
-        chunk(std::true_type{});
-        while (base >= kTraceChunk) {
-#pragma unroll
-            for (int j = 0; j < kTraceChunk; ++j) wc[j] = wn[j];
+        walk(wa, sa, wb, sb, std::true_type{});
+        for (;;) {
             base -= kTraceChunk;
-            prefetch();
-            chunk(std::false_type{});
+            if (base < 0) break;
+            load(wa, base - kTraceChunk);
+            l2_prefetch(base - 4 * kTraceChunk);
+            walk(wb, sb, wa, sa, std::false_type{});
+            base -= kTraceChunk;
+            if (base < 0) break;
+            load(wb, base - kTraceChunk);
+            l2_prefetch(base - 4 * kTraceChunk);
+            walk(wa, sa, wb, sb, std::false_type{});
         }
     }
     __syncwarp();
