@@ -281,18 +281,25 @@ __device__ __forceinline__ void argmin_phase(const typename MP::T (&r)[CD::S], t
 // a private shared-memory ring with cp.async (LDGSTS, 16 B pieces, 128 B = one group at a time,
 // two groups ahead of the consumer), and the ACS loop reads its step with one conflict-free LDS.128.
 // No cross-lane sharing, hence no barrier: cp.async.wait_group is all the synchronisation needed.
-template <int M, int B>
+// PB = bytes per cp.async piece.  PB = 16: one LDGSTS per 4 metrics, a lane's piece is 16 contiguous bytes, so
+// the scalar operand loads of a warp hit 8 banks (4-way conflict).  PB = 4: one LDGSTS per metric (cp.async.ca),
+// words interleaved across lanes, every operand load is conflict-free.  Measured (gpurun_out/call_r1o.log): the four
+// times more LDGSTS requests cost far more than the conflicts (n = 2: 107.5 -> 85.7 Gbit/s, n = 3: 68.0 -> 35.7),
+// so PB = 16 is the default for both; PB = 4 stays selectable for A/B builds (VDEC_RING_PB_M4 / _M8).
+template <int M, int B, int PB>
 struct SoftRing {
     static constexpr int kStepBytes = M * 4;
-    static constexpr int kPieces = kStepBytes / 16;            // 16-byte pieces per step (M = 4, 8)
+    static constexpr int kPieces = kStepBytes / PB;            // pieces per step
     static constexpr int G = B;                                // steps per prefetch group = one rotation period,
                                                                // so the prefetch sits at phase 0 only (no per-step test)
     static constexpr int NG = 3;                               // groups in the ring
     static constexpr int kSlots = G * NG;
     static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * kStepBytes;   // K=7, n=2: 9 KB
     static_assert(M == 4 || M == 8, "soft ring feeder supports n = 2, 3");
+    static_assert(PB == 16 || PB == 4, "piece size");
 
-    static constexpr uint32_t kGroupBytes = (uint32_t)G * kPieces * 512;   // ring bytes of one group (all 32 lanes)
+    static constexpr uint32_t kPieceStride = 32 * PB;                      // ring bytes of one piece (all 32 lanes)
+    static constexpr uint32_t kGroupBytes = (uint32_t)G * kPieces * kPieceStride;   // ring bytes of one group
 
     uint32_t base;        // shared-window address of this lane's first piece
     uint32_t T;
@@ -301,32 +308,34 @@ struct SoftRing {
     uint32_t woff;        // ring byte offset where that group goes
     uint32_t roff;        // ring byte offset of the group being consumed
 
+    template <int OFF_S, int OFF_G>
+    static __device__ __forceinline__ void copy_piece(uint32_t dst, const float* src) {
+        if constexpr (PB == 16)
+            asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(OFF_S), "n"(OFF_G) : "memory");
+        else
+            asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 4;" ::"r"(dst), "l"(src), "n"(OFF_S), "n"(OFF_G) : "memory");
+    }
     // Everything is kept incrementally (pointer, step, ring offsets) and the copies of a full group use
     // immediate offsets, so a period pays G*kPieces LDGSTS plus a handful of adds for its input.
     __device__ __forceinline__ void prefetch_next() {
         const uint32_t dst = base + woff;
         if (next_t + G <= T) {
             static_for<0, G * kPieces>([&](auto ic) {
-                constexpr int I = decltype(ic)::value, s = I / kPieces, c = I % kPieces;
-                asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;"
-                             ::"r"(dst), "l"(nextp), "n"((s * kPieces + c) * 512), "n"((s * M + c * 4) * 4) : "memory");
+                constexpr int I = decltype(ic)::value;
+                copy_piece<I * (int)kPieceStride, I * PB>(dst, nextp);
             });
         } else {
-#pragma unroll
-            for (int s = 0; s < G; ++s)
-                if (next_t + s < T) {
-#pragma unroll
-                    for (int c = 0; c < kPieces; ++c)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                                     ::"r"(dst + (s * kPieces + c) * 512), "l"(nextp + s * M + c * 4) : "memory");
-                }
+            static_for<0, G * kPieces>([&](auto ic) {
+                constexpr int I = decltype(ic)::value, s = I / kPieces;
+                if (next_t + s < T) copy_piece<I * (int)kPieceStride, I * PB>(dst, nextp);
+            });
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         nextp += G * M; next_t += G;
         woff = (woff == (NG - 1) * kGroupBytes) ? 0u : woff + kGroupBytes;
     }
     __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
-        base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * 16;
+        base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * PB;
         T = steps; nextp = row; next_t = 0; woff = 0; roff = 0;
         prefetch_next();
         prefetch_next();
@@ -337,6 +346,9 @@ struct SoftRing {
         asm volatile("cp.async.wait_group 2;" ::: "memory");
     }
     __device__ __forceinline__ void end_period() { roff = (roff == (NG - 1) * kGroupBytes) ? 0u : roff + kGroupBytes; }
+    // ring byte offset (immediate) of metric x of step PH of the current group
+    template <int PH>
+    VDEC_HD static constexpr int elem_off(int x) { return ((PH * M + x) * 4 / PB) * (int)kPieceStride + ((PH * M + x) * 4) % PB; }
     // packed mode: fetch every operand pair (bm[x], bm[y]) that MASK names straight into a 64-bit
     // register pair with two scalar loads.  Volatile so that ptxas neither fuses them into a v4 load
     // (which pins four consecutive registers and costs two MOVs per FADD2 operand) nor drops them.
@@ -347,8 +359,8 @@ struct SoftRing {
             constexpr int I = decltype(ic)::value, x = I / M, y = I % M;
             if constexpr ((MASK >> I) & 1ull) {
                 float lo, hi;
-                asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(lo) : "r"(a), "n"((PH * kPieces + x / 4) * 512 + 4 * (x % 4)));
-                asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(hi) : "r"(a), "n"((PH * kPieces + y / 4) * 512 + 4 * (y % 4)));
+                asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(lo) : "r"(a), "n"(elem_off<PH>(x)));
+                asm volatile("ld.volatile.shared.f32 %0, [%1+%2];" : "=f"(hi) : "r"(a), "n"(elem_off<PH>(y)));
                 asm("mov.b64 %0, {%1, %2};" : "=l"(bp[I]) : "f"(lo), "f"(hi));
             } else {
                 bp[I] = 0;
@@ -376,7 +388,13 @@ struct HardDirect {
 };
 
 template <class MP, int M, int B> struct FeederOf;
-template <int M, int B> struct FeederOf<SoftF32, M, B> { using type = SoftRing<M, B>; };
+#ifndef VDEC_RING_PB_M4
+#define VDEC_RING_PB_M4 16
+#endif
+#ifndef VDEC_RING_PB_M8
+#define VDEC_RING_PB_M8 16
+#endif
+template <int M, int B> struct FeederOf<SoftF32, M, B> { using type = SoftRing<M, B, (M == 8 ? VDEC_RING_PB_M8 : VDEC_RING_PB_M4)>; };
 template <int M, int B> struct FeederOf<HardU16, M, B> { using type = HardDirect<M, B>; };
 
 #ifndef VDEC_TRACE_CHUNK
