@@ -67,7 +67,7 @@ def write_octave(path: str, name: str, points) -> None:
     with open(path, "a") as f:
         f.write("snr_%s = [%s];\n" % (name, " ".join("%g" % p["ebn0_db"] for p in points)))
         f.write("bits_%s = [%s];\n" % (name, " ".join("%d" % p["bits"] for p in points)))
-        f.write("ber_%s = [%s];\n" % (name, " ".join("%.10f" % p["ber"] for p in points)))
+        f.write("ber_%s = [%s];\n" % (name, " ".join("%.6e" % p["ber"] for p in points)))
 
 
 def simulate_awgn_point(dec, total_frames: int, ebn0_db: float, seed: int, rank: int = 0, world: int = 1,

@@ -32,8 +32,8 @@ def main():
         ("C2h hard K7 r1/2 L1024", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, 0),
         ("C2h hard K7 r1/2 L1024 (32-bit kernel)", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, cc.PREFER_32BIT),
         ("f3 quant K7 r1/2 L1024 (u8 metrics <= 7)", C.K7_R12, cc.SOFT_U8, cc.PARITY_LINEAR, 1000000 // q, 0),
-        ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, (1 << 18) // q, 0),
-        ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, (1 << 18) // q, 0),
+        ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, 511488 // q, 0),
+        ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, 511488 // q, 0),
         ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),
         ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, 0),
         ("C4 soft K9 L1024 ref-labels (table-driven)", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 16384 // q, 0),
