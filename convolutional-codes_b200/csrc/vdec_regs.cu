@@ -21,6 +21,10 @@ using CB1 = CodeDef<4, 2, 0xB000000000000000ull, 0xE000000000000000ull, 0, true>
 using CB2 = CodeDef<5, 2, 0xA800000000000000ull, 0xF000000000000000ull, 0, true>;   // :28-31
 using CB3 = CodeDef<6, 2, 0xB400000000000000ull, 0xE800000000000000ull, 0, true>;   // :35-38
 using CB5 = CodeDef<3, 3, 0xA000000000000000ull, 0xC000000000000000ull, 0x2000000000000000ull, true>;   // :50-54
+// textbook (true parity) labels of the codebook entries that have a D^3 tap (0 and 5 have none: one table serves both modes)
+using CB1L = CodeDef<4, 2, 0xB000000000000000ull, 0xE000000000000000ull, 0, false>;
+using CB2L = CodeDef<5, 2, 0xA800000000000000ull, 0xF000000000000000ull, 0, false>;
+using CB3L = CodeDef<6, 2, 0xB400000000000000ull, 0xE800000000000000ull, 0, false>;
 
 static const RegsEntry g_entries[] = {
     make_regs_entry<K7R12Ref, SoftF32>("regs_soft_f32<K7 (171,133) ref-labels>"),
@@ -32,6 +36,9 @@ static const RegsEntry g_entries[] = {
     make_regs_entry<CB2, SoftF32>("regs_soft_f32<codebook2 K5>"),
     make_regs_entry<CB3, SoftF32>("regs_soft_f32<codebook3 K6>"),
     make_regs_entry<CB5, SoftF32>("regs_soft_f32<codebook5 K3 r1/3>"),
+    make_regs_entry<CB1L, SoftF32>("regs_soft_f32<codebook1 K4 linear>"),
+    make_regs_entry<CB2L, SoftF32>("regs_soft_f32<codebook2 K5 linear>"),
+    make_regs_entry<CB3L, SoftF32>("regs_soft_f32<codebook3 K6 linear>"),
     make_regs_entry<K7R12Ref, HardU16>("regs_hard_u16<K7 (171,133) ref-labels>"),
     make_regs_entry<K7R12Lin, HardU16>("regs_hard_u16<K7 (171,133) linear>"),
     make_regs_entry<CB0, HardU16>("regs_hard_u16<codebook0 K3>"),
@@ -39,6 +46,9 @@ static const RegsEntry g_entries[] = {
     make_regs_entry<CB2, HardU16>("regs_hard_u16<codebook2 K5>"),
     make_regs_entry<CB3, HardU16>("regs_hard_u16<codebook3 K6>"),
     make_regs_entry<CB5, HardU16>("regs_hard_u16<codebook5 K3 r1/3>"),
+    make_regs_entry<CB1L, HardU16>("regs_hard_u16<codebook1 K4 linear>"),
+    make_regs_entry<CB2L, HardU16>("regs_hard_u16<codebook2 K5 linear>"),
+    make_regs_entry<CB3L, HardU16>("regs_hard_u16<codebook3 K6 linear>"),
 };
 
 int regs_count() { return (int)(sizeof(g_entries) / sizeof(g_entries[0])); }

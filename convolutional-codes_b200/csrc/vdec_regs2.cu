@@ -14,6 +14,9 @@ using CB1 = CodeDef<4, 2, 0xB000000000000000ull, 0xE000000000000000ull, 0, true>
 using CB2 = CodeDef<5, 2, 0xA800000000000000ull, 0xF000000000000000ull, 0, true>;   // :28-31
 using CB3 = CodeDef<6, 2, 0xB400000000000000ull, 0xE800000000000000ull, 0, true>;   // :35-38
 using CB5 = CodeDef<3, 3, 0xA000000000000000ull, 0xC000000000000000ull, 0x2000000000000000ull, true>;   // :50-54
+using CB1L = CodeDef<4, 2, 0xB000000000000000ull, 0xE000000000000000ull, 0, false>;  // true-parity labels (D^3 tap present)
+using CB2L = CodeDef<5, 2, 0xA800000000000000ull, 0xF000000000000000ull, 0, false>;
+using CB3L = CodeDef<6, 2, 0xB400000000000000ull, 0xE800000000000000ull, 0, false>;
 
 static const Regs2Entry g_entries2[] = {
     make_regs2_entry<K7R12Ref, kModeHard>("regs2_hard_u16x2<K7 (171,133) ref-labels>"),
@@ -25,12 +28,18 @@ static const Regs2Entry g_entries2[] = {
     make_regs2_entry<CB2, kModeHard>("regs2_hard_u16x2<codebook2 K5>"),
     make_regs2_entry<CB3, kModeHard>("regs2_hard_u16x2<codebook3 K6>"),
     make_regs2_entry<CB5, kModeHard>("regs2_hard_u16x2<codebook5 K3 r1/3>"),
+    make_regs2_entry<CB1L, kModeHard>("regs2_hard_u16x2<codebook1 K4 linear>"),
+    make_regs2_entry<CB2L, kModeHard>("regs2_hard_u16x2<codebook2 K5 linear>"),
+    make_regs2_entry<CB3L, kModeHard>("regs2_hard_u16x2<codebook3 K6 linear>"),
     make_regs2_entry<K7R12Ref, kModeQuant>("regs2_soft_u8x2<K7 (171,133) ref-labels>"),
     make_regs2_entry<K7R12Lin, kModeQuant>("regs2_soft_u8x2<K7 (171,133) linear>"),
     make_regs2_entry<CB0, kModeQuant>("regs2_soft_u8x2<codebook0 K3>"),
     make_regs2_entry<CB1, kModeQuant>("regs2_soft_u8x2<codebook1 K4>"),
     make_regs2_entry<CB2, kModeQuant>("regs2_soft_u8x2<codebook2 K5>"),
     make_regs2_entry<CB3, kModeQuant>("regs2_soft_u8x2<codebook3 K6>"),
+    make_regs2_entry<CB1L, kModeQuant>("regs2_soft_u8x2<codebook1 K4 linear>"),
+    make_regs2_entry<CB2L, kModeQuant>("regs2_soft_u8x2<codebook2 K5 linear>"),
+    make_regs2_entry<CB3L, kModeQuant>("regs2_soft_u8x2<codebook3 K6 linear>"),
 };
 
 const Regs2Entry* regs2_find(uint32_t K, uint32_t n, uint32_t mode, const uint8_t* labels) {

@@ -89,6 +89,8 @@ def test_soft_vs_oracle(cc, orc, torch_cuda, key, L, F, sigma, parity):
     assert np.array_equal(out, exp), f"{name}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
     if parity == 1 and code.K >= 9:
         assert name.startswith("tile_soft_f32"), name
+    if code.K <= 7:
+        assert name.startswith("regs_soft_f32"), name
     if code.K <= 11:   # the table-driven kernel must agree too
         out2, name2 = _decode_soft(cc, torch_cuda, code, parity, met, flags=cc.FORCE_GENERIC)
         assert name2.startswith("generic") and np.array_equal(out2, exp)
@@ -118,7 +120,7 @@ def test_hard_vs_oracle(cc, orc, torch_cuda, key, L, F, p, parity):
         assert np.array_equal(out2, exp) and np.array_equal(pm2, exp_pm), name2
         out3, pm3, name3 = _decode_hard(cc, torch_cuda, code, parity, sym, flags=cc.PREFER_32BIT)   # both register kernel families
         assert np.array_equal(out3, exp) and np.array_equal(pm3, exp_pm), name3
-        if L <= 1024 and (parity == 0 or key.startswith("k7")):      # labellings the register kernels are instantiated for
+        if L <= 1024:
             assert name.startswith("regs2_hard_u16x2"), name
             assert key == "k7r13" or name3.startswith("regs_hard_u16"), name3   # (no 32-bit instantiation of the n=3 K=7 code)
 
