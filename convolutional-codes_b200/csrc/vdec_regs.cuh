@@ -55,9 +55,13 @@ struct CodeDef {
 constexpr int kRegsThreads = 128;
 
 // compile-time loop: f(integral_constant<int, I>) for I in [I0, N)
+template <int I0, class F, int... Is>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
+    (f(std::integral_constant<int, I0 + Is>{}), ...);
+}
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+    if constexpr (I < N) static_for_impl<I>(f, std::make_integer_sequence<int, N - I>{});
 }
 
 // ---- metric policies -----------------------------------------------------------------------
@@ -209,6 +213,26 @@ VDEC_HD constexpr uint64_t used_pairs_mask() {
         }
     }
     return m;
+}
+
+// the same question for label alphabets larger than 8 (M*M > 64): is operand pair I = x*M + y needed at phase PH?
+template <class CD, int PH>
+VDEC_HD constexpr bool pair_used(int I) {
+    constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M;
+    for (int q = 0; q < S / 2; ++q) {
+        if (PB == 0) {
+            const uint32_t u = rotr_bits(2 * q, PH, B), v = u + 1;
+            for (uint32_t i = 0; i < 2; ++i) if ((int)(CD::label(u, i) * M + CD::label(v, i)) == I) return true;
+        } else {
+            if ((q >> (PB - 1)) & 1) continue;
+            const uint32_t u0 = rotr_bits(2 * q, PH, B), u1 = rotr_bits(2 * q + 1, PH, B);
+            for (uint32_t i = 0; i < 2; ++i) {
+                if ((int)(CD::label(u0, i) * M + CD::label(u1, i)) == I) return true;
+                if ((int)(CD::label(u0 + 1, i) * M + CD::label(u1 + 1, i)) == I) return true;
+            }
+        }
+    }
+    return false;
 }
 
 template <class CD, int PH>

@@ -1,5 +1,6 @@
 // vdec_tile.cu — registry of register-tile kernels for K = 9 .. 15 (see vdec_tile.cuh).
-// Linear labels only; a request matches when its host-computed label table equals the entry's.
+// True-parity labels and the reference's de-facto labels; a request matches when its host-computed label table
+// equals the entry's.
 #include <string.h>
 
 #include "vdec_tile.cuh"
@@ -14,6 +15,12 @@ using T13 = TileDef<13, 0x8AD8000000000000ull, 0xFD88000000000000ull>;    // (10
 using T14 = TileDef<14, 0x8EF4000000000000ull, 0xB94C000000000000ull>;    // (21675,27123)_8
 using T15 = TileDef<15, 0x99A2000000000000ull, 0xA572000000000000ull>;    // (46321,51271)_8 — BASELINE config 4
 
+// the reference's de-facto labelling of the same polynomials (they carry taps at register positions 4 mod 8)
+using T9R  = TileDef<9,  0xB880000000000000ull, 0xF580000000000000ull, true>;
+using T11R = TileDef<11, 0x9BA0000000000000ull, 0xF620000000000000ull, true>;
+using T13R = TileDef<13, 0x8AD8000000000000ull, 0xFD88000000000000ull, true>;
+using T15R = TileDef<15, 0x99A2000000000000ull, 0xA572000000000000ull, true>;
+
 static const TileEntry* entries(int* count) {
     static const TileEntry e[] = {
         make_tile_entry<T9>("tile_soft_f32<K9 (561,753) linear, 4 threads/frame>"),
@@ -23,6 +30,10 @@ static const TileEntry* entries(int* count) {
         make_tile_entry<T13>("tile_soft_f32<K13 (10533,17661) linear, 64 threads/frame>"),
         make_tile_entry<T14>("tile_soft_f32<K14 (21675,27123) linear, 128 threads/frame>"),
         make_tile_entry<T15>("tile_soft_f32<K15 (46321,51271) linear, 256 threads/frame>"),
+        make_tile_entry<T9R>("tile_soft_f32<K9 (561,753) ref-labels, 4 threads/frame>"),
+        make_tile_entry<T11R>("tile_soft_f32<K11 (2335,3661) ref-labels, 16 threads/frame>"),
+        make_tile_entry<T13R>("tile_soft_f32<K13 (10533,17661) ref-labels, 64 threads/frame>"),
+        make_tile_entry<T15R>("tile_soft_f32<K15 (46321,51271) ref-labels, 256 threads/frame>"),
     };
     *count = (int)(sizeof(e) / sizeof(e[0]));
     return e;

@@ -31,14 +31,16 @@ namespace vd {
 
 constexpr int kTileThreads = 256;
 
-constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
+VDEC_HD constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return r; }
 
 #ifndef VDEC_TILE_VB
 #define VDEC_TILE_VB 2
 #endif
 
-template <int K_, uint64_t P0_, uint64_t P1_, int VB_ = VDEC_TILE_VB>
+template <int K_, uint64_t P0_, uint64_t P1_, bool REF_ = false, int VB_ = VDEC_TILE_VB>
 struct TileDef {
+    static constexpr bool REF = REF_;                        // the reference's de-facto (non-linear) parity, vdec_labels.h
+    static constexpr int ML = REF_ ? 16 : 4;                 // size of the LINEAR label alphabet the kernel works in
     static constexpr int VB = VB_, VEC = 1 << VB_;           // registers a reader fetches per LDS (4: LDS.128)
     static constexpr int K = K_, N = 2, M = 4, B = K_ - 1, S = 1 << (K_ - 1), TB = B - 6, TPF = 1 << TB;
     static_assert(K_ >= 9 && K_ <= 15, "register-tile kernel covers K = 9 .. 15");
@@ -53,10 +55,21 @@ struct TileDef {
         return (uint32_t)((((P0_ >> (64 - K_ + k)) & 1ull) << 1) | ((P1_ >> (64 - K_ + k)) & 1ull));
     }
     VDEC_HD static constexpr uint32_t gin() { return (uint32_t)((((P0_ >> 63) & 1ull) << 1) | ((P1_ >> 63) & 1ull)); }
-    VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {
+    // De-facto labels (vdec_labels.h: parity_bit): bit j of the label is forced to 0 when z_j = XOR of the tapped
+    // register bits at positions 4 mod 8 of the 64-bit shift register is set.  z is linear in the state too, so
+    // the kernel carries the 4-bit LINEAR extended label el = parity | z << 2 and maps it to the metric index
+    // (el & 3) & ~(el >> 2) only where the branch metrics are fetched.
+    VDEC_HD static constexpr uint32_t zbit(int k) {
+        const int pos = 64 - K_ + k;
+        if (!REF_ || (pos & 7) != 4) return 0u;
+        return gbit(k);
+    }
+    VDEC_HD static constexpr uint32_t ebit(int k) { return gbit(k) | (zbit(k) << 2); }
+    VDEC_HD static constexpr uint32_t metric_index(uint32_t el) { return (el & 3u) & ~(el >> 2); }
+    VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {          // the n-bit label the decoder compares against
         uint32_t x = i ? gin() : 0u;
-        for (int k = 0; k < B; ++k) if ((s >> k) & 1u) x ^= gbit(k);
-        return x;
+        for (int k = 0; k < B; ++k) if ((s >> k) & 1u) x ^= ebit(k);
+        return metric_index(x);
     }
 
     // ---- exchange address map phi: extended sigma (bits 0..5 register, 6.. region-thread index) -> float index.
@@ -142,11 +155,11 @@ struct TileDef {
 // u = rotr6(register, k) is true logical bit c for c <= 5-k and bit B-6+c above (the bits that wrapped).
 template <class TD, int KS>
 struct TileCode {
-    static constexpr int K = 7, N = 2, B = 6, S = 64, M = 4, NW = 2;
-    VDEC_HD static constexpr uint32_t label(uint32_t u, uint32_t i) {
+    static constexpr int K = 7, N = 2, B = 6, S = 64, M = TD::ML, NW = 2;
+    VDEC_HD static constexpr uint32_t label(uint32_t u, uint32_t i) {          // register part of the (extended) label
         uint32_t x = i ? TD::gin() : 0u;
         for (int c = 0; c < 6; ++c)
-            if ((u >> c) & 1u) x ^= TD::gbit(c <= 5 - KS ? c : TD::B - 6 + c);
+            if ((u >> c) & 1u) x ^= TD::ebit(c <= 5 - KS ? c : TD::B - 6 + c);
         return x;
     }
 };
@@ -158,17 +171,19 @@ __device__ __forceinline__ void tile_group_sync(uint32_t group) {
     else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(TPF) : "memory");
 }
 
-// operand pairs (bm[x ^ xt], bm[y ^ xt]) for the pairs MASK names; slot = shared-window address of the step's 4 floats
-template <uint64_t MASK>
-__device__ __forceinline__ void tile_get_pairs(uint32_t slot, uint32_t xt, uint64_t (&bp)[16]) {
-    const uint32_t bx = slot ^ (xt << 2);
-    const uint32_t a[4] = {bx, bx ^ 4u, bx ^ 8u, bx ^ 12u};
-    static_for<0, 16>([&](auto ic) {
-        constexpr int I = decltype(ic)::value, x = I / 4, y = I % 4;
-        if constexpr ((MASK >> I) & 1ull) {
+// operand pairs (vm[x ^ xt], vm[y ^ xt]) for the label pairs phase KS needs; slot = shared-window address of the
+// step's ML entries (the 4 branch metrics, or their 16-entry expansion by extended label; entries 2^ESH bytes
+// apart), aligned to its size
+template <class CD, int KS, int ESH = 2>
+__device__ __forceinline__ void tile_get_pairs(uint32_t slot, uint32_t xt, uint64_t (&bp)[CD::M * CD::M]) {
+    constexpr int M = CD::M;
+    const uint32_t bx = slot ^ (xt << ESH);
+    static_for<0, M * M>([&](auto ic) {
+        constexpr int I = decltype(ic)::value, x = I / M, y = I % M;
+        if constexpr (pair_used<CD, KS>(I)) {
             float lo, hi;
-            asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(lo) : "r"(a[x]));
-            asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(hi) : "r"(a[y]));
+            asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(lo) : "r"(bx ^ ((uint32_t)x << ESH)));
+            asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(hi) : "r"(bx ^ ((uint32_t)y << ESH)));
             bp[I] = pack2(lo, hi);
         } else {
             bp[I] = 0;
@@ -178,16 +193,21 @@ __device__ __forceinline__ void tile_get_pairs(uint32_t slot, uint32_t xt, uint6
 
 constexpr int kTileRingGroups = 3;                                  // windows of input resident per frame
 constexpr int kTileRingBytes = kTileRingGroups * 6 * 16;            // per frame
+constexpr int kTileVmBytes = 6 * 16 * 4;                            // per frame: one window of metrics expanded by extended label
 
 template <class TD>
 __global__ void __launch_bounds__(kTileThreads, 2)
 vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_t* __restrict__ final_state,
                  uint32_t nframes, uint32_t T, uint32_t stride_steps, uint32_t init_all_from) {
     constexpr int B = TD::B, S = TD::S, TB = TD::TB, TPF = TD::TPF, FPC = TD::FPC, RT = TD::RT;
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    extern __shared__ __align__(1024) unsigned char s_raw[];
     float* xall = reinterpret_cast<float*>(s_raw);                               // [NREG][RT * 64] exchange regions
     unsigned char* rings = s_raw + (size_t)kTileThreads * 64 * 4;               // [FPC][kTileRingBytes]
-    float* red_v = reinterpret_cast<float*>(rings + (size_t)FPC * kTileRingBytes);   // [kTileThreads / 32]
+    // REF: metrics expanded by extended label, [warp or frame][6 steps][16 labels][FPW frames of the warp] floats —
+    // frames interleaved innermost so that the lanes of a warp spread over the banks; aligned for XOR addressing
+    constexpr int FPW = TPF < 32 ? 32 / TPF : 1, FSH = ilog2(FPW);
+    unsigned char* vms = rings + (((size_t)FPC * kTileRingBytes + 511) & ~(size_t)511);
+    float* red_v = reinterpret_cast<float*>(vms + (TD::REF ? (size_t)FPC * kTileVmBytes : 0));   // [kTileThreads / 32]
     uint32_t* red_s = reinterpret_cast<uint32_t*>(red_v + kTileThreads / 32);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -199,18 +219,21 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
     float* xbuf = xall + (size_t)(tid / RT) * RT * 64;
     const uint32_t wbase = TD::wthr(thr), rbase = TD::rthr(thr);
 
-    // thread part of the labels at step position k: tau bit j is sigma bit 6+j = logical bit 6+j-k
+    // thread part of the (extended) labels at step position k: tau bit j is sigma bit 6+j = logical bit 6+j-k
     uint32_t xt[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         uint32_t x = 0;
 #pragma unroll
-        for (int j = 0; j < TB; ++j) x ^= ((tau >> j) & 1u) ? TD::gbit(6 + j - k) : 0u;
+        for (int j = 0; j < TB; ++j) x ^= ((tau >> j) & 1u) ? TD::ebit(6 + j - k) : 0u;
         xt[k] = x;
     }
 
     // input ring of this frame: [group][step][4 floats], filled by the frame's thread 0
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings + (size_t)fic * kTileRingBytes);
+    [[maybe_unused]] const uint32_t fiw = fic & (FPW - 1);                       // frame within its vm group
+    [[maybe_unused]] float* vm = reinterpret_cast<float*>(vms + (size_t)(fic >> FSH) * FPW * kTileVmBytes) + fiw;
+    [[maybe_unused]] const uint32_t vma = (uint32_t)__cvta_generic_to_shared(vm);
     const float* nextp = in + (size_t)fr * stride_steps * 4;
     uint32_t next_t = 0, woff = 0, roff = 0;
     auto prefetch = [&]() {
@@ -240,13 +263,23 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
         prefetch();
         asm volatile("cp.async.wait_group 2;" ::: "memory");
         tile_group_sync<TPF>(fic);                      // ring data visible; the previous exchange has been read by all
+        if constexpr (TD::REF) {                        // expand the window's metrics: vm[step][el] = bm[step][(el & 3) & ~(el >> 2)]
+            const float* raw = reinterpret_cast<const float*>(rings + (size_t)fic * kTileRingBytes) + roff / 4;
+#pragma unroll
+            for (int e = 0; e < (96 + TPF - 1) / TPF; ++e) {
+                const uint32_t i = e * TPF + tau;
+                if (TPF >= 96 ? tau < 96u : i < 96u) vm[(size_t)i << FSH] = raw[(i >> 4) * 4 + TD::metric_index(i & 15u)];
+            }
+            tile_group_sync<TPF>(fic);
+        }
     };
     auto step = [&](auto kc) {
         constexpr int KS = decltype(kc)::value;
         using CD = TileCode<TD, KS>;
-        uint64_t bp[16];
+        uint64_t bp[CD::M * CD::M];
         uint32_t dw[2];
-        tile_get_pairs<used_pairs_mask<CD, KS>()>(ring + roff + KS * 16, xt[KS], bp);
+        if constexpr (TD::REF) tile_get_pairs<CD, KS, 2 + FSH>(vma + KS * (64 << FSH), xt[KS], bp);
+        else tile_get_pairs<CD, KS>(ring + roff + KS * 16, xt[KS], bp);
         acs_step_f2<CD, KS>(rp, bp, dw);
         if (live) sv[(size_t)(t + KS) * TPF] = make_uint2(dw[0], dw[1]);
     };
@@ -372,7 +405,8 @@ template <class TD>
 int tile_launch(const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st) {
     uint2* surv = reinterpret_cast<uint2*>(scratch);
     uint32_t* final_state = reinterpret_cast<uint32_t*>(surv + (size_t)g.nframes * g.T * TD::TPF);
-    const size_t smem = (size_t)kTileThreads * 64 * 4 + (size_t)TD::FPC * kTileRingBytes + (kTileThreads / 32) * 8;
+    const size_t smem = (size_t)kTileThreads * 64 * 4 + (((size_t)TD::FPC * kTileRingBytes + 511) & ~(size_t)511) +
+                        (TD::REF ? (size_t)TD::FPC * kTileVmBytes : 0) + (kTileThreads / 32) * 8;
     auto kern = vit_tile_forward<TD>;
     VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (g.nframes + TD::FPC - 1) / TD::FPC;

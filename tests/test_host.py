@@ -34,14 +34,16 @@ def test_kernel_selection(cc):
     assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regs_soft_f32<K7 (171,133) linear")
     assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_REF, cc.FORCE_GENERIC).startswith("generic_soft_f32")
     # K = 8 .. 12: lane-group register kernel for linear labels, table-driven for the reference's quirk labels
-    assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("generic_soft_f32<K9")
+    assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("tile_soft_f32<K9 (561,753) ref")
+    assert cc.config_kernel_name(cc.codes.K10_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("generic_soft_f32<K10")
     assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regsw_soft_f32<K8")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K9")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, cc.PREFER_LANEGROUP).startswith("regsw_soft_f32<K9")
     assert cc.config_kernel_name(cc.codes.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, cc.PREFER_LANEGROUP).startswith("regsw_soft_f32<K11")
     assert cc.config_kernel_name(cc.codes.K13_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K13")
     assert cc.config_kernel_name(cc.codes.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K15")
-    assert cc.config_kernel_name(cc.codes.K15_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("generic_soft_f32<K15")
+    assert cc.config_kernel_name(cc.codes.K15_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("tile_soft_f32<K15 (46321,51271) ref")
+    assert cc.config_kernel_name(cc.codes.K15_R12, cc.SOFT_F32, cc.PARITY_REF, cc.FORCE_GENERIC).startswith("generic_soft_f32<K15")
     # hard decisions: 32-bit register kernel; packed 16-bit kernel only for labellings the former lacks
     assert cc.config_kernel_name(cc.get_code(0), cc.HARD_U16).startswith("regs2_hard_u16x2<codebook0")
     assert cc.config_kernel_name(cc.get_code(0), cc.HARD_U16, cc.PARITY_REF, cc.PREFER_32BIT).startswith("regs_hard_u16<codebook0")

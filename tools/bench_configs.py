@@ -36,13 +36,15 @@ def main():
         ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, 511488 // q, 0),
         ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),
         ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, 0),
-        ("C4 soft K9 L1024 ref-labels (table-driven)", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 16384 // q, 0),
+        ("C4 soft K9 L1024 ref-labels", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 131072 // q, 0),
+        ("C4 soft K9 L1024 ref-labels (table-driven)", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 16384 // q, cc.FORCE_GENERIC),
         ("C4 soft K11 L1024", C.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 32768 // q, 0),
         ("C4 soft K9 L1024 (lane-group)", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, cc.PREFER_LANEGROUP),
         ("C4 soft K11 L1024 (lane-group)", C.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 32768 // q, cc.PREFER_LANEGROUP),
         ("C4 soft K13 L1024", C.K13_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 9472 // q, 0),
         ("C4 soft K15 L1024", C.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 2368 // q, 0),
-        ("C4 soft K15 L1024 ref-labels (table-driven)", C.K15_R12, cc.SOFT_F32, cc.PARITY_REF, 1024 // q, 0),
+        ("C4 soft K15 L1024 ref-labels", C.K15_R12, cc.SOFT_F32, cc.PARITY_REF, 2368 // q, 0),
+        ("C4 soft K15 L1024 ref-labels (table-driven)", C.K15_R12, cc.SOFT_F32, cc.PARITY_REF, 1024 // q, cc.FORCE_GENERIC),
     ]
     if not args.only or args.only in "stream K7 sliding-window":
         # one unterminated stream of 2^28 steps, windows of 1024 payload + 2x128 overlap steps
