@@ -52,7 +52,10 @@ struct CodeDef {
     }
 };
 
-constexpr int kRegsThreads = 128;
+#ifndef VDEC_REGS_THREADS
+#define VDEC_REGS_THREADS 128
+#endif
+constexpr int kRegsThreads = VDEC_REGS_THREADS;
 
 // compile-time loop: f(integral_constant<int, I>) for I in [I0, N)
 template <int I0, class F, int... Is>
