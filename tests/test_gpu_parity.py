@@ -159,6 +159,32 @@ def test_edge_cases_ties_and_chunking(cc, orc, torch_cuda):
     dec.close()
 
 
+def test_tile_and_packed_kernels_ties_and_chunking(cc, orc, torch_cuda):
+    """the same edge cases through the register-tile kernels (several frames per CTA, several launches per call,
+    integer-valued metrics that tie constantly) and through the packed kernel with an odd number of frames"""
+    rng = np.random.default_rng(1)
+    for key, L, F, mf in (("k9", 100, 150, 67), ("k13", 40, 7, 2), ("k15", 20, 3, 2)):
+        code = _get(cc, key, L)
+        for parity in (0, 1):
+            oc = ocode(code, parity)
+            met = rng.integers(0, 3, size=(F, code.T, code.M)).astype(np.float32)
+            exp = orc.decode_soft(oc, met)
+            out, name = _decode_soft(cc, torch_cuda, code, parity, met, max_frames=mf)
+            assert name.startswith("tile_soft_f32") and np.array_equal(out, exp), name
+            out, _ = _decode_soft(cc, torch_cuda, code, parity, met, max_frames=mf, host=True)
+            assert np.array_equal(out, exp)
+        met = np.ones((3, code.T, code.M), np.float32)
+        out, _ = _decode_soft(cc, torch_cuda, code, 1, met)
+        assert not out.any()
+    code = cc.codes.K7_R12.with_block_len(77)
+    _, sym = make_hard_inputs(orc, ocode(code, 1), 133, 0.06, seed=9)
+    exp, exp_pm = orc.decode_hard(ocode(code, 1), sym)
+    dec = cc.BatchDecoder(code, cc.HARD_U16, 1, max_frames=45)          # 45 + 45 + 43 frames: odd launches for a 2-frames-per-thread kernel
+    out, pm = dec.decode_host(sym)
+    assert dec.kernel_name.startswith("regs2_hard_u16x2") and np.array_equal(out, exp) and np.array_equal(pm, exp_pm)
+    dec.close()
+
+
 def test_headline_config_full_frame_properties(cc, orc, torch_cuda):
     """BASELINE config 2 shape (K=7, L=1024) at a size the oracle cannot cover entirely:
     noise-free round trip, determinism, sharding invariance of the synthetic link, and the error
