@@ -281,6 +281,24 @@ def run_gpu(args) -> int:
         assert np.array_equal(outs[0], out[:ns].cpu().numpy()), "GPU output differs from the CPU oracle on the sample"
         cpu = {"value": ns * code.L / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": f"first {ns} frames of the GPU batch ({dt:.1f} s on one core); GPU output checked bit-exact on them"}
+        # and the UNMODIFIED reference objects (oracle/_ref) on the longest frame their uint8_t interface takes
+        if oracle.reference_available():
+            ref = oracle.Reference()
+            c249 = code.with_block_len(249)
+            o249 = oracle.Code(c249.n, c249.K, c249.L, c249.polynomials, oracle.PARITY_REF)
+            d249 = cc.BatchDecoder(c249, cc.SOFT_F32, cc.PARITY_REF, device=local)
+            nf = 2 * ns
+            _, m249 = d249.synth_awgn(nf, 0, SEED + 1, sigma)
+            g249 = d249.decode(m249).cpu().numpy()
+            h249 = m249.cpu().numpy()
+            t0 = time.perf_counter()
+            r249 = ref.awgn_decode(o249, h249)
+            dt2 = time.perf_counter() - t0
+            assert np.array_equal(r249, g249), "GPU output differs from the compiled reference decoder"
+            cpu["reference_objects"] = {"value": nf * c249.L / dt2 / 1e9, "unit": UNIT, "cores": 1,
+                                        "sample": f"{nf} frames of K=7 (171,133) L=249 through AWGN-channel/viterbi-decoder.c compiled "
+                                                  f"unmodified ({dt2:.1f} s); GPU output bit-exact on all of them"}
+            d249.close()
 
     line = {
         "metric": METRIC, "value": gbit, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
