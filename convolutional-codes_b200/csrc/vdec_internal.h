@@ -102,13 +102,9 @@ struct vdec {
     const vd::Regs2Entry* regs2;   // non-null => packed 16-bit kernel (takes precedence)
     const vd::WideEntry* regsw;    // non-null => lane-group register kernel (K = 8 .. 12)
     const vd::TileEntry* tile;     // non-null => register-tile kernel (K = 9 .. 15)
-    uint32_t* surv;                  // survivor scratch
-    size_t surv_bytes;
-    // host-buffer pipeline (vdec_decode_host)
+    // host-buffer pipeline (vdec_decode_host): two stages, each with its own stream and device staging
     cudaStream_t streams[2];
-    void* pin_in[2]; uint8_t* pin_out[2]; int32_t* pin_pm[2];
     void* dev_in[2]; uint8_t* dev_out[2]; int32_t* dev_pm[2];
-    uint32_t host_chunk;             // frames per pipeline stage
     uint64_t launches;
     char kernel_name[128];
 };

@@ -1,4 +1,4 @@
-// vdec_tile.cu — registry of register-tile kernels for K = 9 .. 15 (see vdec_tile.cuh).
+// vdec_tile.cu — registry of register-tile kernels for K = 8 .. 15 (see vdec_tile.cuh).
 // True-parity labels and the reference's de-facto labels; a request matches when its host-computed label table
 // equals the entry's.
 #include <string.h>
@@ -7,6 +7,8 @@
 
 namespace vd {
 
+using T8  = TileDef<8,  0xF900000000000000ull, 0xA700000000000000ull>;    // (371,247)_8: the largest K the reference can run
+using T8R = TileDef<8,  0xF900000000000000ull, 0xA700000000000000ull, true>;
 using T9  = TileDef<9,  0xB880000000000000ull, 0xF580000000000000ull>;    // (561,753)_8 — BASELINE config 4
 using T10 = TileDef<10, 0x9DC0000000000000ull, 0xD940000000000000ull>;    // (1167,1545)_8
 using T11 = TileDef<11, 0x9BA0000000000000ull, 0xF620000000000000ull>;    // (2335,3661)_8
@@ -23,6 +25,8 @@ using T15R = TileDef<15, 0x99A2000000000000ull, 0xA572000000000000ull, true>;
 
 static const TileEntry* entries(int* count) {
     static const TileEntry e[] = {
+        make_tile_entry<T8>("tile_soft_f32<K8 (371,247) linear, 2 threads/frame>"),
+        make_tile_entry<T8R>("tile_soft_f32<K8 (371,247) ref-labels, 2 threads/frame>"),
         make_tile_entry<T9>("tile_soft_f32<K9 (561,753) linear, 4 threads/frame>"),
         make_tile_entry<T10>("tile_soft_f32<K10 (1167,1545) linear, 8 threads/frame>"),
         make_tile_entry<T11>("tile_soft_f32<K11 (2335,3661) linear, 16 threads/frame>"),
@@ -40,7 +44,7 @@ static const TileEntry* entries(int* count) {
 }
 
 const TileEntry* tile_find(uint32_t K, uint32_t n, uint32_t metric, const uint8_t* labels) {
-    if (metric != VDEC_SOFT_F32 || K < 9 || K > 15) return nullptr;
+    if (metric != VDEC_SOFT_F32 || K < 8 || K > 15) return nullptr;
     int cnt = 0;
     const TileEntry* e = entries(&cnt);
     for (int i = 0; i < cnt; ++i)

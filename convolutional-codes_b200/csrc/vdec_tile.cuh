@@ -1,4 +1,4 @@
-// vdec_tile.cuh — register-tile Viterbi kernel for large trellises (K = 9 .. 15, 256 .. 16384 states).
+// vdec_tile.cuh — register-tile Viterbi kernel for large trellises (K = 8 .. 15, 128 .. 16384 states).
 //
 // Replaces receive_symbol()/traceback() of AWGN-channel/viterbi-decoder.c:108-141, 71-90 for the codes of
 // BASELINE config 4 (K = 9 .. 15, survivor memory in HBM; the reference itself hangs for K >= 9, SURVEY finding 2,
@@ -37,13 +37,14 @@ VDEC_HD constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return
 #define VDEC_TILE_VB 2
 #endif
 
-template <int K_, uint64_t P0_, uint64_t P1_, bool REF_ = false, int VB_ = VDEC_TILE_VB>
+template <int K_, uint64_t P0_, uint64_t P1_, bool REF_ = false, int VB_ = (K_ == 8 ? 1 : VDEC_TILE_VB)>
 struct TileDef {
     static constexpr bool REF = REF_;                        // the reference's de-facto (non-linear) parity, vdec_labels.h
     static constexpr int ML = REF_ ? 16 : 4;                 // size of the LINEAR label alphabet the kernel works in
     static constexpr int VB = VB_, VEC = 1 << VB_;           // registers a reader fetches per LDS (4: LDS.128)
     static constexpr int K = K_, N = 2, M = 4, B = K_ - 1, S = 1 << (K_ - 1), TB = B - 6, TPF = 1 << TB;
-    static_assert(K_ >= 9 && K_ <= 15, "register-tile kernel covers K = 9 .. 15");
+    static_assert(K_ >= 8 && K_ <= 15, "register-tile kernel covers K = 8 .. 15");
+    static_assert(K_ > 8 || VB_ <= 1, "K = 8: the reader's second register bit is a register bit of the writer too, so at most 2 registers per LDS");
     static constexpr int FPC = kTileThreads / TPF;            // frames per CTA
     static constexpr int RT = TPF > 32 ? TPF : 32;            // threads sharing one exchange region
     static constexpr int RTB = ilog2(RT);

@@ -67,6 +67,7 @@ SOFT_CASES = [  # (code getter, L, frames, sigma)
     ("k9", 301, 131, 0.5), ("k10", 64, 70, 0.5), ("k11", 200, 37, 0.5), ("k12", 130, 19, 0.5), ("k12", 1, 9, 0.5),
     ("k13", 77, 6, 0.5), ("k13", 1024, 5, 0.45), ("k14", 50, 5, 0.5), ("k15", 200, 3, 0.5), ("k15", 1, 2, 0.5),
     ("k15", 1024, 2, 0.45), ("k11", 1024, 18, 0.45), ("k9", 6, 70, 0.5), ("k13", 13, 9, 0.5),
+    ("k8", 1024, 200, 0.45), ("k8", 5, 300, 0.5),
 ]
 
 
@@ -87,7 +88,7 @@ def test_soft_vs_oracle(cc, orc, torch_cuda, key, L, F, sigma, parity):
     exp = orc.decode_soft(oc, met)
     out, name = _decode_soft(cc, torch_cuda, code, parity, met)
     assert np.array_equal(out, exp), f"{name}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
-    if code.K >= 9 and (parity == 1 or key in ("k9", "k11", "k13", "k15")):     # de-facto labels: instantiated for these four
+    if code.K >= 8 and (parity == 1 or key in ("k8", "k9", "k11", "k13", "k15")):     # de-facto labels: instantiated for these five
         assert name.startswith("tile_soft_f32"), name
     if code.K <= 7:
         assert name.startswith("regs_soft_f32"), name

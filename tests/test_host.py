@@ -36,7 +36,9 @@ def test_kernel_selection(cc):
     # K = 8 .. 12: lane-group register kernel for linear labels, table-driven for the reference's quirk labels
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("tile_soft_f32<K9 (561,753) ref")
     assert cc.config_kernel_name(cc.codes.K10_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("generic_soft_f32<K10")
-    assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regsw_soft_f32<K8")
+    assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K8")
+    assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("tile_soft_f32<K8 (371,247) ref")
+    assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR, cc.PREFER_LANEGROUP).startswith("regsw_soft_f32<K8")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K9")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, cc.PREFER_LANEGROUP).startswith("regsw_soft_f32<K9")
     assert cc.config_kernel_name(cc.codes.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, cc.PREFER_LANEGROUP).startswith("regsw_soft_f32<K11")

@@ -35,6 +35,8 @@ def main():
         ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, 511488 // q, 0),
         ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, 511488 // q, 0),
         ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),
+        ("K8 soft L1024", C.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 262144 // q, 0),
+        ("K8 soft L1024 (lane-group)", C.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 262144 // q, cc.PREFER_LANEGROUP),
         ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, 0),
         ("C4 soft K9 L1024 ref-labels", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 131072 // q, 0),
         ("C4 soft K9 L1024 ref-labels (table-driven)", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 16384 // q, cc.FORCE_GENERIC),
