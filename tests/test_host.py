@@ -158,3 +158,21 @@ def test_two_rank_counter_allreduce_gloo(cc):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) runs without a GPU and prints
+    one JSON line with the same metric / unit / config keys plus impl, cpu_baseline and a zero-copy e2e object."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "viterbi_decoded_gbit_per_s_k7_r12_soft" and d["unit"] == "Gbit/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["config"]["workload"].startswith("awgn-simulation")
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
