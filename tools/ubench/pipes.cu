@@ -26,14 +26,16 @@ enum { OP_FADD, OP_FADD2, OP_FMNMX, OP_IADD, OP_IMAD, OP_SHF, OP_LOP, OP_SETPSEL
        MIX_F2_MNMX2,  // FADD2 : FMNMX 1:2
        MIX_F2_FADD,   // FADD2 : FADD 1:1
        OP_VIADDMNMX, OP_PRMT, OP_IADD3_3, MIX_VAM_IADD3, MIX_VAM_LOP, MIX_VAM_IMAD, MIX_PACKED,   // packed 16-bit recipe (vdec_regs2.cuh)
+       MIX_FSETP_PFADD, MIX_ISETP_PFADD, MIX_ISETP_FMNMX, MIX_FSETP_FMNMX, MIX_ACS_I, MIX_ACS_FS,   // float vs integer compare for the decision
        NOPS };
 static const char* names[NOPS] = {"FADD", "FADD2", "FMNMX", "IADD3", "IMAD", "SHF", "LOP3", "FSETP+SELP",
   "FADD+FMNMX", "FADD+IADD3", "FADD+IMAD", "FMNMX+IADD3",
   "ACS_A 2FADD+FMNMX+IADD+SHF", "ACS_B 2FADD+FSETP+SELP+@pOR", "ACS_C FADD2+2(FMNMX+IADD+SHF)",
   "ACS_D FADD2+2(FMNMX+FADDdiff+SHF)", "ACS_E FADD2+2(FMNMX+IMADdiff+SHF)", "ACS_F 2FADD+FMNMX+FADDdiff+SHF", "FADD2+FMNMX 1:1", "FADD2+2FMNMX", "FADD2+FADD 1:1",
-  "VIADDMNMX.U16x2", "PRMT", "IADD3 (3-input)", "VIADDMNMX+IADD3", "VIADDMNMX+LOP3", "VIADDMNMX+IMAD", "PACKED 2ADD+2VIADDMNMX+2IADD3+PRMT+LOP3"};
+  "VIADDMNMX.U16x2", "PRMT", "IADD3 (3-input)", "VIADDMNMX+IADD3", "VIADDMNMX+LOP3", "VIADDMNMX+IMAD", "PACKED 2ADD+2VIADDMNMX+2IADD3+PRMT+LOP3",
+  "FSETP+@pFADD", "ISETP+@pFADD", "ISETP+@pFADD+FMNMX", "FSETP+@pFADD+FMNMX", "ACS_I FADD2+2(ISETP+FMNMX+@pFADD)", "ACS_FS FADD2+2(FSETP+FMNMX+@pFADD)"};
 // instructions per chain-iteration for each op
-static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5, 2, 3, 2, 2, 2, 2, 2, 2, 2, 8};
+static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5, 2, 3, 2, 2, 2, 2, 2, 2, 2, 8, 2, 2, 3, 3, 7, 7};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, long long* cyc) {
@@ -126,6 +128,28 @@ __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, lon
         asm volatile("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(p) : "r"(t0), "r"(t1));
         asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(((uint32_t*)&d[i])[0]) : "r"(p), "r"(cu));
         u[i] = n0; v[i] = n1;
+      }
+      if (OP == MIX_FSETP_PFADD) asm volatile("{.reg .pred p; setp.lt.f32 p, %1, %2; @p add.f32 %0, %0, %2;}" : "+f"(f[i]) : "f"(g[i]), "f"(cf));
+      if (OP == MIX_ISETP_PFADD) asm volatile("{.reg .pred p; setp.lt.u32 p, %1, %2; @p add.f32 %0, %0, %3;}" : "+f"(f[i]) : "r"(u[i]), "r"(v[i]), "f"(cf));
+      if (OP == MIX_ISETP_FMNMX) asm volatile("{.reg .pred p; setp.lt.u32 p, %2, %3; min.f32 %1, %1, %4; @p add.f32 %0, %0, %4;}" : "+f"(f[i]), "+f"(g[i]) : "r"(u[i]), "r"(v[i]), "f"(cf));
+      if (OP == MIX_FSETP_FMNMX) asm volatile("{.reg .pred p; setp.lt.f32 p, %1, %2; min.f32 %1, %1, %2; @p add.f32 %0, %0, %2;}" : "+f"(f[i]), "+f"(g[i]) : "f"(cf));
+      if (OP == MIX_ACS_FS) {
+        unsigned long long cc;
+        asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(cc) : "l"(d[i]), "l"(c2));
+        float c0 = __uint_as_float((uint32_t)cc), c1 = __uint_as_float((uint32_t)(cc >> 32));
+        float n0, n1;
+        asm volatile("{.reg .pred p; setp.lt.f32 p, %3, %2; min.f32 %0, %2, %3; @p add.f32 %1, %1, %4;}" : "=f"(n0), "+f"(f[i]) : "f"(c0), "f"(c1), "f"(cf));
+        asm volatile("{.reg .pred p; setp.lt.f32 p, %3, %2; min.f32 %0, %2, %3; @p add.f32 %1, %1, %4;}" : "=f"(n1), "+f"(g[i]) : "f"(c1), "f"(cf), "f"(cf));
+        d[i] = ((unsigned long long)__float_as_uint(n1) << 32) | __float_as_uint(n0);
+      }
+      if (OP == MIX_ACS_I) {
+        unsigned long long cc;
+        asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(cc) : "l"(d[i]), "l"(c2));
+        float c0 = __uint_as_float((uint32_t)cc), c1 = __uint_as_float((uint32_t)(cc >> 32));
+        float n0, n1;
+        asm volatile("{.reg .pred p; setp.lt.u32 p, %3, %2; min.f32 %0, %4, %5; @p add.f32 %1, %1, %6;}" : "=f"(n0), "+f"(f[i]) : "r"(__float_as_uint(c0)), "r"(__float_as_uint(c1)), "f"(c0), "f"(c1), "f"(cf));
+        asm volatile("{.reg .pred p; setp.lt.u32 p, %3, %2; min.f32 %0, %4, %5; @p add.f32 %1, %1, %6;}" : "=f"(n1), "+f"(g[i]) : "r"(__float_as_uint(c1)), "r"(__float_as_uint(cf)), "f"(c1), "f"(cf), "f"(cf));
+        d[i] = ((unsigned long long)__float_as_uint(n1) << 32) | __float_as_uint(n0);
       }
       if (OP == MIX_ACS_F) {
         float c0, c1, e0;
