@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib")
 OBJ = os.path.join(os.path.dirname(HERE), "build", "obj")
 
-CU_SOURCES = ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_generic.cu", "vdec_synth.cu"]
+CU_SOURCES = ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_tile2.cu", "vdec_generic.cu", "vdec_synth.cu"]
 NVCC_FLAGS = ["-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

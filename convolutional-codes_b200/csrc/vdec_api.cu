@@ -51,7 +51,7 @@ static int ensure_scratch(vdec_priv* p, int slot, const vd::LaunchGeom& geom, ui
     vdec* h = &p->base;
     vd::LaunchGeom g = geom;
     g.nframes = frames;
-    const size_t need = h->tile ? vd::tile_bytes(h->tile, g) : h->regsw ? vd::regsw_bytes(h->regsw, g) : h->regs2 ? vd::regs2_bytes(h->regs2, g)
+    const size_t need = h->tile2 ? vd::tile2_bytes(h->tile2, g) : h->tile ? vd::tile_bytes(h->tile, g) : h->regsw ? vd::regsw_bytes(h->regsw, g) : h->regs2 ? vd::regs2_bytes(h->regs2, g)
                         : h->regs ? h->regs->surv_bytes(g) : vd::generic_surv_bytes(g);
     if (need <= p->sc.bytes[slot]) return 0;
     if (p->sc.p[slot]) { VDEC_CUDA(cudaFree(p->sc.p[slot])); p->sc.p[slot] = nullptr; p->sc.bytes[slot] = 0; }
@@ -101,13 +101,14 @@ static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const
         uint8_t* out = out_dev + done * g.out_bytes;
         int32_t* pm = pm_dev ? pm_dev + done : nullptr;
         int rc;
-        if (h->tile) rc = vd::tile_run(h->tile, g, in, out, p->sc.p[slot], st);
+        if (h->tile2) rc = vd::tile2_run(h->tile2, g, in, out, pm, p->sc.p[slot], st);
+        else if (h->tile) rc = vd::tile_run(h->tile, g, in, out, p->sc.p[slot], st);
         else if (h->regsw) rc = vd::regsw_run(h->regsw, g, in, out, p->sc.p[slot], st);
         else if (h->regs2) rc = vd::regs2_run(h->regs2, g, in, out, pm, p->sc.p[slot], st);
         else if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
         else rc = vd::generic_launch(g, h->cfg.metric, h->bfly_labels_dev, in, out, pm, p->sc.p[slot], st);
         if (rc != 0) return -1;
-        h->launches += (!h->tile && (h->regs || h->regs2 || h->regsw)) ? 1 : 2;   // tile, table-driven = forward + traceback
+        h->launches += (!h->tile && !h->tile2 && (h->regs || h->regs2 || h->regsw)) ? 1 : 2;   // tile, table-driven = forward + traceback
         done += n;
     }
     return 0;
@@ -125,10 +126,18 @@ static const char* metric_tag(uint32_t metric) {
 // kernel family for a config: packed 16-bit (integer metrics that provably stay below 2^15) >
 // specialised register kernel > table-driven
 static void select_kernels(const vdec_config* cfg, const uint8_t* labels, const vd::RegsEntry** regs,
-                           const vd::Regs2Entry** regs2, const vd::WideEntry** regsw, const vd::TileEntry** tile) {
-    *regs = nullptr; *regs2 = nullptr; *regsw = nullptr; *tile = nullptr;
+                           const vd::Regs2Entry** regs2, const vd::WideEntry** regsw, const vd::TileEntry** tile,
+                           const vd::Tile2Entry** tile2) {
+    *regs = nullptr; *regs2 = nullptr; *regsw = nullptr; *tile = nullptr; *tile2 = nullptr;
     if (cfg->flags & VDEC_FORCE_GENERIC) return;
     if (cfg->constr_len >= 8) {
+        if (cfg->metric != VDEC_SOFT_F32) {          // integer metrics: packed 16-bit tile kernel when the range allows
+            const uint64_t Ti = (uint64_t)cfg->block_len + cfg->constr_len - 1;
+            const uint64_t mx = cfg->metric == VDEC_HARD_U16 ? cfg->symlen_out : (cfg->metric_max ? cfg->metric_max : 255);
+            if (Ti * mx < 0x4000u)
+                *tile2 = vd::tile2_find(cfg->constr_len, cfg->symlen_out, cfg->metric == VDEC_HARD_U16 ? 0 : 1, labels);
+            return;
+        }
         if (!(cfg->flags & VDEC_PREFER_LANEGROUP) || cfg->constr_len > 12)
             *tile = vd::tile_find(cfg->constr_len, cfg->symlen_out, cfg->metric, labels);
         if (!*tile && (uint64_t)cfg->block_len + cfg->constr_len - 1 <= 65536)
@@ -200,10 +209,11 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
     free(bl);
     if (e != cudaSuccess) { vd::set_error("label upload failed: %s", cudaGetErrorString(e)); vdec_destroy(h); return -1; }
 
-    select_kernels(cfg, h->labels_host, &h->regs, &h->regs2, &h->regsw, &h->tile);
-    if (h->tile) {
-        snprintf(h->kernel_name, sizeof(h->kernel_name), "%s", vd::tile_name(h->tile));
+    select_kernels(cfg, h->labels_host, &h->regs, &h->regs2, &h->regsw, &h->tile, &h->tile2);
+    if (h->tile || h->tile2) {
+        snprintf(h->kernel_name, sizeof(h->kernel_name), "%s", h->tile2 ? vd::tile2_name(h->tile2) : vd::tile_name(h->tile));
         // bound the survivor scratch of one launch to ~8 GiB (S/8 bytes per step and frame)
+        // (the packed kernels store the decisions of two frames in the same words: same bytes per frame)
         size_t cap = ((size_t)8 << 30) / ((size_t)g.T * (g.S / 8));
         if (cap < 1) cap = 1;
         if (cap > (1u << 20)) cap = 1u << 20;
@@ -278,9 +288,10 @@ const char* vdec_config_kernel_name(const struct vdec_config* cfg) {
     uint8_t labels[2 * 16384];
     if (vdec_config_labels(cfg, labels) != 0) return "";
     const vd::RegsEntry* e = nullptr; const vd::Regs2Entry* e2 = nullptr; const vd::WideEntry* ew = nullptr;
-    const vd::TileEntry* et = nullptr;
-    select_kernels(cfg, labels, &e, &e2, &ew, &et);
-    if (et) snprintf(name, sizeof(name), "%s", vd::tile_name(et));
+    const vd::TileEntry* et = nullptr; const vd::Tile2Entry* et2 = nullptr;
+    select_kernels(cfg, labels, &e, &e2, &ew, &et, &et2);
+    if (et2) snprintf(name, sizeof(name), "%s", vd::tile2_name(et2));
+    else if (et) snprintf(name, sizeof(name), "%s", vd::tile_name(et));
     else if (ew) snprintf(name, sizeof(name), "%s", vd::regsw_name(ew));
     else if (e2) snprintf(name, sizeof(name), "%s", vd::regs2_name(e2));
     else if (e) snprintf(name, sizeof(name), "%s", e->name);

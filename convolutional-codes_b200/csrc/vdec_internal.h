@@ -69,6 +69,14 @@ const char* tile_name(const TileEntry* e);
 int tile_run(const TileEntry* e, const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st);
 size_t tile_bytes(const TileEntry* e, const LaunchGeom& g);
 
+// ---- packed 16-bit register-tile kernels for K = 8 .. 15 (vdec_tile2.cu): hard decisions, quantised soft ----
+struct Tile2Entry;
+const Tile2Entry* tile2_find(uint32_t K, uint32_t n, uint32_t mode, const uint8_t* labels);
+const char* tile2_name(const Tile2Entry* e);
+int tile2_run(const Tile2Entry* e, const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* scratch,
+              cudaStream_t st);
+size_t tile2_bytes(const Tile2Entry* e, const LaunchGeom& g);
+
 // ---- generic table-driven kernels (vdec_generic.cu) ----------------------------------------
 // One CTA per frame, path metrics in shared memory, labels from a device table; any K <= 15.
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
@@ -101,7 +109,8 @@ struct vdec {
     const vd::RegsEntry* regs;     // non-null => specialised kernel
     const vd::Regs2Entry* regs2;   // non-null => packed 16-bit kernel (takes precedence)
     const vd::WideEntry* regsw;    // non-null => lane-group register kernel (K = 8 .. 12)
-    const vd::TileEntry* tile;     // non-null => register-tile kernel (K = 9 .. 15)
+    const vd::TileEntry* tile;     // non-null => register-tile kernel (K = 8 .. 15, fp32 soft metrics)
+    const vd::Tile2Entry* tile2;   // non-null => packed 16-bit register-tile kernel (K = 8 .. 15, integer metrics)
     // host-buffer pipeline (vdec_decode_host): two stages, each with its own stream and device staging
     cudaStream_t streams[2];
     void* dev_in[2]; uint8_t* dev_out[2]; int32_t* dev_pm[2];

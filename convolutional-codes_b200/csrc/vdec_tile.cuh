@@ -364,7 +364,7 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
 // (cur & (2^(5-k) - 1)) | (cur >> (B-1-k)) << (5-k) of thread (cur >> (5-k)) & (TPF-1)'s word; the thread index is
 // the same for every step of a window, so a window's words are fetched together.  Output as in vdec_regs.cuh:
 // the state doubles as a shift register of decoded bits, 16 of which are emitted every 16 steps (:81-89).
-__global__ void __launch_bounds__(128)
+static __global__ void __launch_bounds__(128)
 vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ final_state, uint8_t* __restrict__ out,
                    uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t B, uint32_t TPF) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;

@@ -103,7 +103,10 @@ def test_soft_vs_oracle(cc, orc, torch_cuda, key, L, F, sigma, parity):
 HARD_CASES = [("cb0", 17000, 9, 0.05),      # too long for the shared-memory output tile: table-driven kernels
               ("cb0", 40, 1001, 0.0125), ("cb0", 40, 1000, 0.2), ("cb1", 40, 300, 0.05), ("cb3", 40, 100, 0.05),
               ("cb5", 40, 257, 0.1), ("k7r12", 249, 70, 0.05), ("k7r12", 1024, 40, 0.04), ("k7r13", 100, 33, 0.1),
-              ("k9", 100, 8, 0.05), ("k15", 30, 2, 0.03)]
+              ("k9", 100, 8, 0.05), ("k15", 30, 2, 0.03),
+              # packed 16-bit register-tile kernels: odd frame counts, every window remainder, several pairs per warp / CTA
+              ("k8", 200, 133, 0.05), ("k8", 3, 5, 0.1), ("k9", 1024, 77, 0.04), ("k9", 7, 300, 0.1), ("k11", 150, 21, 0.05),
+              ("k13", 64, 9, 0.05), ("k15", 100, 3, 0.04), ("k15", 1024, 2, 0.03)]
 
 
 @pytest.mark.parametrize("key,L,F,p", HARD_CASES, ids=[f"{c[0]}-L{c[1]}-p{c[3]}" for c in HARD_CASES])
@@ -116,6 +119,11 @@ def test_hard_vs_oracle(cc, orc, torch_cuda, key, L, F, p, parity):
     out, pm, name = _decode_hard(cc, torch_cuda, code, parity, sym)
     assert np.array_equal(out, exp), name
     assert np.array_equal(pm, exp_pm), name
+    if code.K >= 8 and (parity == 1 or key in ("k8", "k9")):
+        assert name.startswith("tile2_hard_u16x2"), name
+        if code.L <= 200:   # the table-driven kernel must agree too
+            out2, pm2, name2 = _decode_hard(cc, torch_cuda, code, parity, sym, flags=cc.FORCE_GENERIC)
+            assert name2.startswith("generic") and np.array_equal(out2, exp) and np.array_equal(pm2, exp_pm), name2
     if code.K <= 7:
         out2, pm2, name2 = _decode_hard(cc, torch_cuda, code, parity, sym, flags=cc.FORCE_GENERIC)
         assert np.array_equal(out2, exp) and np.array_equal(pm2, exp_pm), name2
@@ -321,7 +329,7 @@ def test_quantised_mode_reproduces_reference_on_hard_demapped_metrics(cc, torch_
 
 
 @pytest.mark.parametrize("key,L,F,qmax", [("k7r12", 1024, 333, 7), ("k7r12", 200, 65, 31), ("cb3", 40, 129, 3), ("cb0", 40, 1000, 2),
-                                           ("cb5", 40, 64, 5), ("k9", 64, 5, 9)])
+                                           ("cb5", 40, 64, 5), ("k9", 64, 5, 9), ("k9", 500, 101, 7), ("k15", 60, 3, 15)])
 @pytest.mark.parametrize("parity", [0, 1], ids=["ref", "linear"])
 def test_quantised_mode_vs_oracle(cc, orc, torch_cuda, key, L, F, qmax, parity):
     code = _get(cc, key, L)
@@ -334,6 +342,8 @@ def test_quantised_mode_vs_oracle(cc, orc, torch_cuda, key, L, F, qmax, parity):
     exp = orc.decode_soft(oc, q.astype(np.float32))                   # the float decoder on the same integers
     out, name = _decode_quant(cc, torch_cuda, code, parity, q, qmax)
     assert np.array_equal(out, exp), name
+    if key == "k9" or (key == "k15" and parity == 1):
+        assert name.startswith("tile2_soft_u8x2"), name
     out, name = _decode_quant(cc, torch_cuda, code, parity, q, 0, flags=cc.FORCE_GENERIC)
     assert name.startswith("generic_soft_u8") and np.array_equal(out, exp)
 

@@ -52,6 +52,13 @@ def test_kernel_selection(cc):
     assert cc.config_kernel_name(cc.codes.K7_R13, cc.HARD_U16).startswith("regs2_hard_u16x2<K7 (133,171,165) ref")
     # frames too long for the shared-memory output tile go to the table-driven kernels
     assert cc.config_kernel_name(cc.get_code(0).with_block_len(20000), cc.HARD_U16).startswith("generic_hard_u16")
+    # integer metrics on large trellises: packed 16-bit register-tile kernels
+    assert cc.config_kernel_name(cc.codes.K8_R12, cc.HARD_U16, cc.PARITY_REF).startswith("tile2_hard_u16x2<K8 (371,247) ref")
+    assert cc.config_kernel_name(cc.codes.K9_R12, cc.HARD_U16, cc.PARITY_LINEAR).startswith("tile2_hard_u16x2<K9")
+    assert cc.config_kernel_name(cc.codes.K15_R12, cc.HARD_U16, cc.PARITY_LINEAR).startswith("tile2_hard_u16x2<K15")
+    assert cc.config_kernel_name(cc.codes.K15_R12, cc.HARD_U16, cc.PARITY_REF).startswith("generic_hard_u16<K15")
+    assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_U8, cc.PARITY_LINEAR, metric_max=7).startswith("tile2_soft_u8x2<K9")
+    assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_U8, cc.PARITY_LINEAR, metric_max=255).startswith("generic_soft_u8<K9")
     # quantised soft mode: packed kernel if the caller bounds the metrics, table-driven otherwise
     assert cc.config_kernel_name(k7, cc.SOFT_U8, metric_max=2).startswith("regs2_soft_u8x2<K7 (171,133) ref")
     assert cc.config_kernel_name(k7, cc.SOFT_U8).startswith("generic_soft_u8")

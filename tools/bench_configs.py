@@ -40,6 +40,10 @@ def main():
         ("C4 soft K9 L1024", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, 0),
         ("C4 soft K9 L1024 ref-labels", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 131072 // q, 0),
         ("C4 soft K9 L1024 ref-labels (table-driven)", C.K9_R12, cc.SOFT_F32, cc.PARITY_REF, 16384 // q, cc.FORCE_GENERIC),
+        ("K9 hard L1024", C.K9_R12, cc.HARD_U16, cc.PARITY_LINEAR, 262144 // q, 0),
+        ("K9 hard L1024 (table-driven)", C.K9_R12, cc.HARD_U16, cc.PARITY_LINEAR, 16384 // q, cc.FORCE_GENERIC),
+        ("K9 quant L1024 (u8 metrics <= 7)", C.K9_R12, cc.SOFT_U8, cc.PARITY_LINEAR, 262144 // q, 0),
+        ("K15 hard L1024", C.K15_R12, cc.HARD_U16, cc.PARITY_LINEAR, 4736 // q, 0),
         ("C4 soft K11 L1024", C.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 32768 // q, 0),
         ("C4 soft K9 L1024 (lane-group)", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, cc.PREFER_LANEGROUP),
         ("C4 soft K11 L1024 (lane-group)", C.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 32768 // q, cc.PREFER_LANEGROUP),

@@ -22,8 +22,8 @@ def comp(n):
     return o
 
 
-with cf.ThreadPoolExecutor(7) as ex:
-    objs = list(ex.map(comp, ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_generic.cu", "vdec_synth.cu"]))
+with cf.ThreadPoolExecutor(8) as ex:
+    objs = list(ex.map(comp, ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_tile2.cu", "vdec_generic.cu", "vdec_synth.cu"]))
 subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", os.path.join(out, "libvdec.so"), *objs,
                 "-Xlinker", "-Bsymbolic"], check=True)
 print("built", out)
