@@ -4,10 +4,10 @@ The product is ``lib/libvdec.so`` (hand-written sm_100a CUDA + a plain C ABI, ``
 the two legacy shim libraries; this package is the thin host-side mirror used by tests and bench.
 """
 from . import codes
-from .codes import (CodeParam, FORCE_GENERIC, PREFER_LANEGROUP, PREFER_32BIT, HARD_U16, PARITY_LINEAR, PARITY_REF, SOFT_F32, SOFT_U8, awgn_sigma, get_code)
-from .decoder import BatchDecoder, LegacyDecoder, VdecError, config_kernel_name, config_labels, demap
+from .codes import (CodeParam, FORCE_GENERIC, PREFER_LANEGROUP, PREFER_32BIT, NO_JIT, HARD_U16, PARITY_LINEAR, PARITY_REF, SOFT_F32, SOFT_U8, awgn_sigma, get_code)
+from .decoder import BatchDecoder, LegacyDecoder, VdecError, config_kernel_name, config_labels, demap, jit_check
 from .link import allreduce_counters, ber_with_ci, shard_range, simulate_awgn_point, sweep_awgn, write_octave
 
 __all__ = ["codes", "CodeParam", "get_code", "awgn_sigma", "BatchDecoder", "LegacyDecoder", "VdecError",
-           "config_labels", "config_kernel_name", "demap", "shard_range", "allreduce_counters",
-           "simulate_awgn_point", "sweep_awgn", "write_octave", "ber_with_ci", "PARITY_REF", "PARITY_LINEAR", "SOFT_F32", "SOFT_U8", "HARD_U16", "FORCE_GENERIC", "PREFER_LANEGROUP", "PREFER_32BIT"]
+           "config_labels", "config_kernel_name", "jit_check", "demap", "shard_range", "allreduce_counters",
+           "simulate_awgn_point", "sweep_awgn", "write_octave", "ber_with_ci", "PARITY_REF", "PARITY_LINEAR", "SOFT_F32", "SOFT_U8", "HARD_U16", "FORCE_GENERIC", "PREFER_LANEGROUP", "PREFER_32BIT", "NO_JIT"]

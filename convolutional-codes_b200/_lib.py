@@ -22,6 +22,7 @@ EXPORTS = {
     "vdec_last_error": (C.c_char_p, []),
     "vdec_config_labels": (C.c_int, [C.POINTER(VdecConfig), C.c_void_p]),
     "vdec_config_kernel_name": (C.c_char_p, [C.POINTER(VdecConfig)]),
+    "vdec_jit_check": (C.c_long, [C.POINTER(VdecConfig)]),
     "vdec_steps": (C.c_uint32, [C.c_void_p]),
     "vdec_states": (C.c_uint32, [C.c_void_p]),
     "vdec_in_bytes_per_frame": (C.c_size_t, [C.c_void_p]),

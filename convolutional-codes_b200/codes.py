@@ -18,6 +18,7 @@ SOFT_U8 = 2        # quantised soft: small integer branch metrics, uint8 [F][T][
 FORCE_GENERIC = 1
 PREFER_32BIT = 4       # hard decisions: 32-bit register kernel instead of the packed 16-bit one
 PREFER_LANEGROUP = 2   # K = 8 .. 12: shuffle-exchange lane-group kernel instead of the register-tile kernel
+NO_JIT = 8             # unregistered polynomials: table-driven kernels instead of a kernel compiled at run time (NVRTC)
 
 
 def left_align(octal: str, K: int) -> int:

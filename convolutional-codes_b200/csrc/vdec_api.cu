@@ -51,7 +51,7 @@ static int ensure_scratch(vdec_priv* p, int slot, const vd::LaunchGeom& geom, ui
     vdec* h = &p->base;
     vd::LaunchGeom g = geom;
     g.nframes = frames;
-    const size_t need = h->tile2 ? vd::tile2_bytes(h->tile2, g) : h->tile ? vd::tile_bytes(h->tile, g) : h->regsw ? vd::regsw_bytes(h->regsw, g) : h->regs2 ? vd::regs2_bytes(h->regs2, g)
+    const size_t need = h->jit ? vd::jit_bytes(h->jit, g) : h->tile2 ? vd::tile2_bytes(h->tile2, g) : h->tile ? vd::tile_bytes(h->tile, g) : h->regsw ? vd::regsw_bytes(h->regsw, g) : h->regs2 ? vd::regs2_bytes(h->regs2, g)
                         : h->regs ? h->regs->surv_bytes(g) : vd::generic_surv_bytes(g);
     if (need <= p->sc.bytes[slot]) return 0;
     if (p->sc.p[slot]) { VDEC_CUDA(cudaFree(p->sc.p[slot])); p->sc.p[slot] = nullptr; p->sc.bytes[slot] = 0; }
@@ -101,14 +101,16 @@ static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const
         uint8_t* out = out_dev + done * g.out_bytes;
         int32_t* pm = pm_dev ? pm_dev + done : nullptr;
         int rc;
-        if (h->tile2) rc = vd::tile2_run(h->tile2, g, in, out, pm, p->sc.p[slot], st);
+        if (h->jit) rc = vd::jit_run(h->jit, g, in, out, pm, p->sc.p[slot], st);
+        else if (h->tile2) rc = vd::tile2_run(h->tile2, g, in, out, pm, p->sc.p[slot], st);
         else if (h->tile) rc = vd::tile_run(h->tile, g, in, out, p->sc.p[slot], st);
         else if (h->regsw) rc = vd::regsw_run(h->regsw, g, in, out, p->sc.p[slot], st);
         else if (h->regs2) rc = vd::regs2_run(h->regs2, g, in, out, pm, p->sc.p[slot], st);
         else if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
         else rc = vd::generic_launch(g, h->cfg.metric, h->bfly_labels_dev, in, out, pm, p->sc.p[slot], st);
         if (rc != 0) return -1;
-        h->launches += (!h->tile && !h->tile2 && (h->regs || h->regs2 || h->regsw)) ? 1 : 2;   // tile, table-driven = forward + traceback
+        h->launches += h->jit ? vd::jit_launches(h->jit)
+                                : (!h->tile && !h->tile2 && (h->regs || h->regs2 || h->regsw)) ? 1 : 2;   // tile, table-driven = forward + traceback
         done += n;
     }
     return 0;
@@ -210,8 +212,18 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
     if (e != cudaSuccess) { vd::set_error("label upload failed: %s", cudaGetErrorString(e)); vdec_destroy(h); return -1; }
 
     select_kernels(cfg, h->labels_host, &h->regs, &h->regs2, &h->regsw, &h->tile, &h->tile2);
-    if (h->tile || h->tile2) {
-        snprintf(h->kernel_name, sizeof(h->kernel_name), "%s", h->tile2 ? vd::tile2_name(h->tile2) : vd::tile_name(h->tile));
+    int jit_family = 0; uint32_t jit_mode = 0;
+    if (!h->regs && !h->regs2 && !h->regsw && !h->tile && !h->tile2 &&
+        vd::jit_pick(cfg, h->labels_host, &jit_family, &jit_mode, nullptr, 0)) {
+        // polynomials outside the registries: compile the matching kernel family for them (vdec_jit.cu)
+        char why[2048] = "";
+        h->jit = vd::jit_get(cfg, jit_family, jit_mode, why, sizeof(why));
+        if (!h->jit && why[0] && getenv("VDEC_QUIET") == nullptr)
+            fprintf(stderr, "[vdec] run-time compilation unavailable, using the table-driven kernels: %s\n", why);
+    }
+    const bool jit_tile = h->jit && vd::jit_launches(h->jit) == 2;
+    if (h->tile || h->tile2 || jit_tile) {
+        snprintf(h->kernel_name, sizeof(h->kernel_name), "%s", h->jit ? vd::jit_name(h->jit) : h->tile2 ? vd::tile2_name(h->tile2) : vd::tile_name(h->tile));
         // bound the survivor scratch of one launch to ~8 GiB (S/8 bytes per step and frame)
         // (the packed kernels store the decisions of two frames in the same words: same bytes per frame)
         size_t cap = ((size_t)8 << 30) / ((size_t)g.T * (g.S / 8));
@@ -219,9 +231,9 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
         if (cap > (1u << 20)) cap = 1u << 20;
         h->max_frames = cfg->max_frames ? cfg->max_frames : (uint32_t)cap;
         if (h->max_frames > cap) h->max_frames = (uint32_t)cap;
-    } else if (h->regs2 || h->regs || h->regsw) {
+    } else if (h->regs2 || h->regs || h->regsw || h->jit) {
         snprintf(h->kernel_name, sizeof(h->kernel_name), "%s",
-                 h->regsw ? vd::regsw_name(h->regsw) : h->regs2 ? vd::regs2_name(h->regs2) : h->regs->name);
+                 h->jit ? vd::jit_name(h->jit) : h->regsw ? vd::regsw_name(h->regsw) : h->regs2 ? vd::regs2_name(h->regs2) : h->regs->name);
         h->max_frames = cfg->max_frames ? cfg->max_frames : (1u << 20);
     } else {
         snprintf(h->kernel_name, sizeof(h->kernel_name), "generic_%s<K%u n%u table-driven>",
@@ -295,8 +307,26 @@ const char* vdec_config_kernel_name(const struct vdec_config* cfg) {
     else if (ew) snprintf(name, sizeof(name), "%s", vd::regsw_name(ew));
     else if (e2) snprintf(name, sizeof(name), "%s", vd::regs2_name(e2));
     else if (e) snprintf(name, sizeof(name), "%s", e->name);
-    else snprintf(name, sizeof(name), "generic_%s<K%u n%u table-driven>", metric_tag(cfg->metric), cfg->constr_len, cfg->symlen_out);
+    else {
+        int family = 0; uint32_t mode = 0;
+        if (!vd::jit_pick(cfg, labels, &family, &mode, name, sizeof(name)))
+            snprintf(name, sizeof(name), "generic_%s<K%u n%u table-driven>", metric_tag(cfg->metric), cfg->constr_len, cfg->symlen_out);
+    }
     return name;
+}
+
+long vdec_jit_check(const struct vdec_config* cfg) {
+    static thread_local uint8_t labels[2 * 16384];
+    if (vdec_config_labels(cfg, labels) != 0) return -1;
+    const vd::RegsEntry* e = nullptr; const vd::Regs2Entry* e2 = nullptr; const vd::WideEntry* ew = nullptr;
+    const vd::TileEntry* et = nullptr; const vd::Tile2Entry* et2 = nullptr;
+    select_kernels(cfg, labels, &e, &e2, &ew, &et, &et2);
+    int family = 0; uint32_t mode = 0;
+    if (e || e2 || ew || et || et2 || !vd::jit_pick(cfg, labels, &family, &mode, nullptr, 0)) return 0;
+    char why[2048] = "";
+    const long n = vd::jit_compile_check(cfg, family, mode, why, sizeof(why));
+    if (n < 0) vd::set_error("run-time compilation failed: %s", why);
+    return n;
 }
 
 int vdec_labels(const vdec_t* h, uint8_t* labels) {

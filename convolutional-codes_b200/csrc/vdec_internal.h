@@ -1,14 +1,22 @@
 // vdec_internal.h — shared between the translation units of libvdec.so (not installed).
+//
+// The kernel headers (vdec_regs.cuh, vdec_tile.cuh, ...) are also compiled at run time by NVRTC for codes outside the
+// built-in registries (vdec_jit.cu); under __CUDACC_RTC__ only the device-side declarations below are visible.
 #pragma once
+#ifdef __CUDACC_RTC__
+#include "vdec.h"
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
 
 #include "../../include/vdec.h"
+#endif
 #include "vdec_labels.h"
 
 namespace vd {
 
+#ifndef __CUDACC_RTC__
 void set_error(const char* fmt, ...);
 
 #define VDEC_CUDA(call)                                                                   \
@@ -19,6 +27,8 @@ void set_error(const char* fmt, ...);
             return -1;                                                                    \
         }                                                                                 \
     } while (0)
+
+#endif  // !__CUDACC_RTC__
 
 // Geometry of one decode launch, passed by value to the kernels.
 struct LaunchGeom {
@@ -32,6 +42,7 @@ struct LaunchGeom {
                              // state, sliding-window blocks); 0xFFFFFFFF = every frame starts in state 0
 };
 
+#ifndef __CUDACC_RTC__
 // ---- code-specialised register kernels (vdec_regs.cu) -------------------------------------
 // One thread per frame, all S <= 64 path metrics in registers, labels are compile-time
 // constants.  An entry serves a request when its label table equals the requested code's.
@@ -77,6 +88,19 @@ int tile2_run(const Tile2Entry* e, const LaunchGeom& g, const void* in, uint8_t*
               cudaStream_t st);
 size_t tile2_bytes(const Tile2Entry* e, const LaunchGeom& g);
 
+// ---- run-time compiled instantiations of the four families above (vdec_jit.cu, NVRTC) -----------------------
+struct JitEntry;
+enum { kJitRegs = 0, kJitRegs2 = 1, kJitTile = 2, kJitTile2 = 3 };
+bool jit_enabled(const vdec_config* cfg);
+bool jit_pick(const vdec_config* cfg, const uint8_t* labels, int* family, uint32_t* mode, char* name, size_t name_len);
+const JitEntry* jit_get(const vdec_config* cfg, int family, uint32_t mode, char* err, size_t errlen);
+const char* jit_name(const JitEntry* e);
+int jit_launches(const JitEntry* e);
+size_t jit_bytes(const JitEntry* e, const LaunchGeom& g);
+int jit_run(const JitEntry* e, const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* scratch,
+            cudaStream_t st);
+long jit_compile_check(const vdec_config* cfg, int family, uint32_t mode, char* err, size_t errlen);
+
 // ---- generic table-driven kernels (vdec_generic.cu) ----------------------------------------
 // One CTA per frame, path metrics in shared memory, labels from a device table; any K <= 15.
 int generic_launch(const LaunchGeom& g, uint32_t metric, const uint32_t* bfly_labels_dev, const void* in,
@@ -95,8 +119,11 @@ int synth_awgn_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t n
 int synth_bsc_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t nframes, uint64_t first_frame,
                      uint64_t seed, uint32_t crossover_ppm, uint8_t* payload, uint8_t* symbols, cudaStream_t st);
 
+#endif  // !__CUDACC_RTC__
+
 }  // namespace vd
 
+#ifndef __CUDACC_RTC__
 // The opaque handle of include/vdec.h
 struct vdec {
     vdec_config cfg;
@@ -111,9 +138,11 @@ struct vdec {
     const vd::WideEntry* regsw;    // non-null => lane-group register kernel (K = 8 .. 12)
     const vd::TileEntry* tile;     // non-null => register-tile kernel (K = 8 .. 15, fp32 soft metrics)
     const vd::Tile2Entry* tile2;   // non-null => packed 16-bit register-tile kernel (K = 8 .. 15, integer metrics)
+    const vd::JitEntry* jit;       // non-null => a kernel of one of these families compiled at run time for this code
     // host-buffer pipeline (vdec_decode_host): two stages, each with its own stream and device staging
     cudaStream_t streams[2];
     void* dev_in[2]; uint8_t* dev_out[2]; int32_t* dev_pm[2];
     uint64_t launches;
     char kernel_name[128];
 };
+#endif  // !__CUDACC_RTC__

@@ -621,28 +621,50 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     }
 }
 
-template <class CD, class MP>
-int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
-    using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
+#ifndef __CUDACC_RTC__
+// ---- host side ------------------------------------------------------------------------------------
+// Launch shape of vit_regs_kernel as a function of (K, n, metric) only, so that kernels compiled at run time
+// (vdec_jit.cu) are launched by the same code as the built-in instantiations.
+struct RegsShape {
+    uint32_t nw;            // survivor words per step and frame
+    size_t ring_bytes;      // input ring per warp
+};
+inline RegsShape regs_shape(uint32_t K, uint32_t n, uint32_t metric) {
+    const uint32_t S = 1u << (K - 1), M = 1u << n;
+    return RegsShape{(S + 31) / 32, metric == VDEC_SOFT_F32 ? (size_t)(K - 1) * 3 * 32 * M * 4 : 0};
+}
+
+// `kern` is a __global__ symbol of this library or a cudaKernel_t of a run-time compiled module
+inline int regs_launch_kernel(const void* kern, const RegsShape& sh, const LaunchGeom& g, const void* in, uint8_t* out,
+                              int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
     uint32_t stage_words = (g.out_bytes + 3) / 4;
     if ((stage_words & 1) == 0) ++stage_words;                 // odd stride: conflict-free column writes
     size_t warp_smem = (size_t)32 * stage_words * 4;
-    const size_t ring_bytes = Feeder::kWarpBytes;
-    if (ring_bytes > warp_smem) warp_smem = ring_bytes;
+    if (sh.ring_bytes > warp_smem) warp_smem = sh.ring_bytes;
     const size_t smem = (size_t)(kRegsThreads / 32) * warp_smem;
-    auto kern = vit_regs_kernel<CD, MP>;
     if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (g.nframes + kRegsThreads - 1) / kRegsThreads;
-    kern<<<blocks, kRegsThreads, smem, st>>>(static_cast<const typename MP::In*>(in), out, path_metric, surv,
-                                              g.nframes, g.T, g.out_bytes, stage_words, g.stride_steps, g.init_all_from);
-    VDEC_CUDA(cudaGetLastError());
+    uint32_t nframes = g.nframes, T = g.T, out_bytes = g.out_bytes, stride = g.stride_steps, init_all_from = g.init_all_from;
+    void* args[] = {&in, &out, &path_metric, &surv, &nframes, &T, &out_bytes, &stage_words, &stride, &init_all_from};
+    VDEC_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kRegsThreads), args, smem, st));
     return 0;
 }
 
-template <class CD>
-size_t regs_surv_bytes(const LaunchGeom& g) {
-    return (size_t)((g.nframes + 31) / 32) * g.T * 32 * CD::NW * sizeof(uint32_t);
+inline size_t regs_surv_bytes_nw(const LaunchGeom& g, uint32_t nw) {
+    return (size_t)((g.nframes + 31) / 32) * g.T * 32 * nw * sizeof(uint32_t);
 }
+
+template <class CD, class MP>
+int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
+    using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
+    constexpr RegsShape sh{(uint32_t)CD::NW, Feeder::kWarpBytes};
+    static_assert(Feeder::kWarpBytes == (MP::kMetric == VDEC_SOFT_F32 ? (size_t)CD::B * 3 * 32 * CD::M * 4 : 0),
+                  "regs_shape() must describe the feeder");
+    return regs_launch_kernel(reinterpret_cast<const void*>(&vit_regs_kernel<CD, MP>), sh, g, in, out, path_metric, surv, st);
+}
+
+template <class CD>
+size_t regs_surv_bytes(const LaunchGeom& g) { return regs_surv_bytes_nw(g, CD::NW); }
 
 template <class CD, class MP>
 RegsEntry make_regs_entry(const char* name) {
@@ -653,5 +675,6 @@ RegsEntry make_regs_entry(const char* name) {
     e.surv_bytes = &regs_surv_bytes<CD>;
     return e;
 }
+#endif  // !__CUDACC_RTC__
 
 }  // namespace vd

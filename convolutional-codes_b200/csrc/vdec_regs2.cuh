@@ -257,6 +257,7 @@ vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t
     }
 }
 
+#ifndef __CUDACC_RTC__
 struct Regs2Entry {
     const char* name;
     uint32_t K, n, mode;
@@ -266,24 +267,32 @@ struct Regs2Entry {
 };
 const Regs2Entry* regs2_find(uint32_t K, uint32_t n, uint32_t mode, const uint8_t* labels);
 
-template <class CD>
-size_t regs2_scratch_bytes(const LaunchGeom& g) {
+inline size_t regs2_scratch_bytes_nw(const LaunchGeom& g, uint32_t nw) {
     const size_t warps = ((size_t)(g.nframes + 1) / 2 + 31) / 32;
-    return warps * g.T * 32 * Surv2<CD::S>::NW * sizeof(uint32_t);                       // survivors
+    return warps * g.T * 32 * nw * sizeof(uint32_t);                                     // survivors
+}
+inline uint32_t regs2_nw(uint32_t K) { return ((1u << (K - 1)) + 15) / 16; }
+
+template <class CD>
+size_t regs2_scratch_bytes(const LaunchGeom& g) { return regs2_scratch_bytes_nw(g, Surv2<CD::S>::NW); }
+
+// `kern` is a __global__ symbol of this library or a cudaKernel_t of a run-time compiled module (vdec_jit.cu)
+inline int regs2_launch_kernel(const void* kern, const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric,
+                               uint32_t* scratch, cudaStream_t st) {
+    const size_t npairs = ((size_t)g.nframes + 1) / 2;
+    uint32_t tile_bytes = (64 * g.out_bytes + 15) & ~15u;
+    const size_t smem = (size_t)(kRegsThreads / 32) * tile_bytes;
+    if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t blocks = (uint32_t)((npairs + kRegsThreads - 1) / kRegsThreads);
+    uint32_t nframes = g.nframes, T = g.T, out_bytes = g.out_bytes, stride = g.stride_steps, init_all_from = g.init_all_from;
+    void* args[] = {&in, &out, &path_metric, &scratch, &nframes, &T, &out_bytes, &tile_bytes, &stride, &init_all_from};
+    VDEC_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kRegsThreads), args, smem, st));
+    return 0;
 }
 
 template <class CD, int MODE>
 int regs2_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* scratch, cudaStream_t st) {
-    const size_t npairs = ((size_t)g.nframes + 1) / 2;
-    const uint32_t tile_bytes = (64 * g.out_bytes + 15) & ~15u;
-    const size_t smem = (size_t)(kRegsThreads / 32) * tile_bytes;
-    auto kern = vit_regs2_kernel<CD, MODE>;
-    if (smem > 48 * 1024) VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t blocks = (uint32_t)((npairs + kRegsThreads - 1) / kRegsThreads);
-    kern<<<blocks, kRegsThreads, smem, st>>>(in, out, path_metric, scratch, g.nframes, g.T, g.out_bytes, tile_bytes,
-                                              g.stride_steps, g.init_all_from);
-    VDEC_CUDA(cudaGetLastError());
-    return 0;
+    return regs2_launch_kernel(reinterpret_cast<const void*>(&vit_regs2_kernel<CD, MODE>), g, in, out, path_metric, scratch, st);
 }
 
 template <class CD, int MODE>
@@ -295,5 +304,6 @@ Regs2Entry make_regs2_entry(const char* name) {
     e.scratch_bytes = &regs2_scratch_bytes<CD>;
     return e;
 }
+#endif  // !__CUDACC_RTC__
 
 }  // namespace vd

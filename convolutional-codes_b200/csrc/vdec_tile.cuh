@@ -397,27 +397,46 @@ vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ 
     }
 }
 
-template <class TD>
-size_t tile_surv_bytes(const LaunchGeom& g) {
-    return (size_t)g.nframes * g.T * TD::TPF * sizeof(uint2) + (size_t)g.nframes * sizeof(uint32_t);
+#ifndef __CUDACC_RTC__
+// ---- host side ------------------------------------------------------------------------------------
+// Launch shape as a function of (K, label mode) only: kernels compiled at run time (vdec_jit.cu) go through the same launcher.
+struct TileShape {
+    uint32_t B, TPF, FPC;
+    bool ref;
+};
+inline TileShape tile_shape(uint32_t K, bool ref) {
+    const uint32_t tpf = 1u << (K - 7);
+    return TileShape{K - 1, tpf, (uint32_t)kTileThreads / tpf, ref};
+}
+inline size_t tile_surv_bytes_tpf(const LaunchGeom& g, uint32_t tpf) {
+    return (size_t)g.nframes * g.T * tpf * sizeof(uint2) + (size_t)g.nframes * sizeof(uint32_t);
+}
+
+// `kern`: vit_tile_forward<TD> of this library or a cudaKernel_t of a run-time compiled module
+inline int tile_launch_kernel(const void* kern, const TileShape& sh, const LaunchGeom& g, const void* in, uint8_t* out,
+                              uint32_t* scratch, cudaStream_t st) {
+    uint2* surv = reinterpret_cast<uint2*>(scratch);
+    uint32_t* final_state = reinterpret_cast<uint32_t*>(surv + (size_t)g.nframes * g.T * sh.TPF);
+    const size_t smem = (size_t)kTileThreads * 64 * 4 + (((size_t)sh.FPC * kTileRingBytes + 511) & ~(size_t)511) +
+                        (sh.ref ? (size_t)sh.FPC * kTileVmBytes : 0) + (kTileThreads / 32) * 8;
+    VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t blocks = (g.nframes + sh.FPC - 1) / sh.FPC;
+    const float* inf = static_cast<const float*>(in);
+    uint32_t nframes = g.nframes, T = g.T, stride = g.stride_steps, init_all_from = g.init_all_from;
+    void* args[] = {&inf, &surv, &final_state, &nframes, &T, &stride, &init_all_from};
+    VDEC_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kTileThreads), args, smem, st));
+    vit_tile_traceback<<<(g.nframes + 127) / 128, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
+    VDEC_CUDA(cudaGetLastError());
+    return 0;
 }
 
 template <class TD>
+size_t tile_surv_bytes(const LaunchGeom& g) { return tile_surv_bytes_tpf(g, TD::TPF); }
+
+template <class TD>
 int tile_launch(const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st) {
-    uint2* surv = reinterpret_cast<uint2*>(scratch);
-    uint32_t* final_state = reinterpret_cast<uint32_t*>(surv + (size_t)g.nframes * g.T * TD::TPF);
-    const size_t smem = (size_t)kTileThreads * 64 * 4 + (((size_t)TD::FPC * kTileRingBytes + 511) & ~(size_t)511) +
-                        (TD::REF ? (size_t)TD::FPC * kTileVmBytes : 0) + (kTileThreads / 32) * 8;
-    auto kern = vit_tile_forward<TD>;
-    VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t blocks = (g.nframes + TD::FPC - 1) / TD::FPC;
-    kern<<<blocks, kTileThreads, smem, st>>>(static_cast<const float*>(in), surv, final_state, g.nframes, g.T,
-                                             g.stride_steps, g.init_all_from);
-    VDEC_CUDA(cudaGetLastError());
-    vit_tile_traceback<<<(g.nframes + 127) / 128, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes,
-                                                               (uint32_t)TD::B, (uint32_t)TD::TPF);
-    VDEC_CUDA(cudaGetLastError());
-    return 0;
+    return tile_launch_kernel(reinterpret_cast<const void*>(&vit_tile_forward<TD>),
+                              TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF}, g, in, out, scratch, st);
 }
 
 struct TileEntry {
@@ -439,5 +458,21 @@ template <class TD>
 TileEntry make_tile_entry(const char* name) {
     return TileEntry{name, (uint32_t)TD::K, (uint32_t)TD::N, tile_labels<TD>(), &tile_launch<TD>, &tile_surv_bytes<TD>};
 }
+
+// Labels of the kernel's label model (TileDef::label) for run-time polynomials: a run-time compiled kernel serves a
+// request only when this equals the table computed from the caller's polynomials (vdec_labels.h).
+inline void tile_model_labels(uint32_t K, uint64_t p0, uint64_t p1, bool ref, uint8_t* labels) {
+    const uint32_t B = K - 1, S = 1u << B;
+    auto gbit = [&](int k) { return (uint32_t)((((p0 >> (64 - K + k)) & 1ull) << 1) | ((p1 >> (64 - K + k)) & 1ull)); };
+    auto ebit = [&](int k) { const int pos = 64 - (int)K + k; return gbit(k) | ((ref && (pos & 7) == 4) ? gbit(k) << 2 : 0u); };
+    const uint32_t gin = (uint32_t)((((p0 >> 63) & 1ull) << 1) | ((p1 >> 63) & 1ull));
+    for (uint32_t s = 0; s < S; ++s)
+        for (uint32_t i = 0; i < 2; ++i) {
+            uint32_t x = i ? gin : 0u;
+            for (uint32_t k = 0; k < B; ++k) if ((s >> k) & 1u) x ^= ebit((int)k);
+            labels[2 * s + i] = (uint8_t)((x & 3u) & ~(x >> 2));
+        }
+}
+#endif  // !__CUDACC_RTC__
 
 }  // namespace vd

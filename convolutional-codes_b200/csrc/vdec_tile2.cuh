@@ -225,27 +225,37 @@ vit_tile2_traceback(const uint4* __restrict__ surv, const uint32_t* __restrict__
     }
 }
 
-template <class TD>
-size_t tile2_surv_bytes(const LaunchGeom& g) {
+#ifndef __CUDACC_RTC__
+inline size_t tile2_surv_bytes_tpf(const LaunchGeom& g, uint32_t tpf) {
     const size_t pairs = ((size_t)g.nframes + 1) / 2;
-    return pairs * g.T * TD::TPF * sizeof(uint4) + (size_t)g.nframes * sizeof(uint32_t);
+    return pairs * g.T * tpf * sizeof(uint4) + (size_t)g.nframes * sizeof(uint32_t);
 }
+
+// `kern`: vit_tile2_forward<TD, MODE> of this library or a cudaKernel_t of a run-time compiled module (vdec_jit.cu)
+inline int tile2_launch_kernel(const void* kern, const TileShape& sh, const LaunchGeom& g, const void* in, uint8_t* out,
+                               int32_t* path_metric, uint32_t* scratch, cudaStream_t st) {
+    const size_t pairs = ((size_t)g.nframes + 1) / 2;
+    uint4* surv = reinterpret_cast<uint4*>(scratch);
+    uint32_t* final_state = reinterpret_cast<uint32_t*>(surv + pairs * g.T * sh.TPF);
+    const size_t smem = (size_t)kTileThreads * 64 * 4 + (sh.ref ? (size_t)sh.FPC * kTileVmBytes : 0) + (kTileThreads / 32) * 16;
+    VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t blocks = (uint32_t)((pairs + sh.FPC - 1) / sh.FPC);
+    uint32_t nframes = g.nframes, T = g.T, stride = g.stride_steps, init_all_from = g.init_all_from;
+    void* args[] = {&in, &surv, &final_state, &path_metric, &nframes, &T, &stride, &init_all_from};
+    VDEC_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kTileThreads), args, smem, st));
+    vit_tile2_traceback<<<(g.nframes + 127) / 128, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
+    VDEC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <class TD>
+size_t tile2_surv_bytes(const LaunchGeom& g) { return tile2_surv_bytes_tpf(g, TD::TPF); }
 
 template <class TD, int MODE>
 int tile2_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* scratch, cudaStream_t st) {
-    const size_t pairs = ((size_t)g.nframes + 1) / 2;
-    uint4* surv = reinterpret_cast<uint4*>(scratch);
-    uint32_t* final_state = reinterpret_cast<uint32_t*>(surv + pairs * g.T * TD::TPF);
-    const size_t smem = (size_t)kTileThreads * 64 * 4 + (TD::REF ? (size_t)TD::FPC * kTileVmBytes : 0) + (kTileThreads / 32) * 16;
-    auto kern = vit_tile2_forward<TD, MODE>;
-    VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t blocks = (uint32_t)((pairs + TD::FPC - 1) / TD::FPC);
-    kern<<<blocks, kTileThreads, smem, st>>>(in, surv, final_state, path_metric, g.nframes, g.T, g.stride_steps, g.init_all_from);
-    VDEC_CUDA(cudaGetLastError());
-    vit_tile2_traceback<<<(g.nframes + 127) / 128, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes,
-                                                                (uint32_t)TD::B, (uint32_t)TD::TPF);
-    VDEC_CUDA(cudaGetLastError());
-    return 0;
+    return tile2_launch_kernel(reinterpret_cast<const void*>(&vit_tile2_forward<TD, MODE>),
+                               TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF}, g, in, out, path_metric,
+                               scratch, st);
 }
 
 struct Tile2Entry {
@@ -260,5 +270,6 @@ template <class TD, int MODE>
 Tile2Entry make_tile2_entry(const char* name) {
     return Tile2Entry{name, (uint32_t)TD::K, (uint32_t)TD::N, (uint32_t)MODE, tile_labels<TD>(), &tile2_launch<TD, MODE>, &tile2_surv_bytes<TD>};
 }
+#endif  // !__CUDACC_RTC__
 
 }  // namespace vd

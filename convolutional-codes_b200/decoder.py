@@ -50,6 +50,16 @@ def config_kernel_name(code: CodeParam, metric: int, parity: int = PARITY_REF, f
     return lib.vdec_config_kernel_name(C.byref(cfg)).decode()
 
 
+def jit_check(code: CodeParam, metric: int, parity: int = PARITY_REF, flags: int = 0, metric_max: int = 0) -> int:
+    """Compile (NVRTC, no GPU needed) the kernel an unregistered code would get; cubin bytes, 0 = nothing to compile."""
+    lib = _lib.load()
+    cfg = make_config(code, metric, parity, flags=flags, metric_max=metric_max)
+    n = lib.vdec_jit_check(C.byref(cfg))
+    if n < 0:
+        raise VdecError(_lib.last_error())
+    return int(n)
+
+
 class BatchDecoder:
     """One decoder object per (code, metric, parity, device) — ``decoder_create`` + ``decoder_init``."""
 

@@ -57,8 +57,10 @@ enum vdec_flags {
     VDEC_FORCE_GENERIC = 1u,    /* never pick a code-specialised kernel (testing) */
     VDEC_PREFER_LANEGROUP = 2u, /* K = 8 .. 12: take the shuffle-exchange lane-group kernel instead of the
                                    shared-memory register-tile kernel (A/B measurements, testing) */
-    VDEC_PREFER_32BIT = 4u      /* hard decisions: take the 32-bit register kernel instead of the packed 16-bit one
+    VDEC_PREFER_32BIT = 4u,     /* hard decisions: take the 32-bit register kernel instead of the packed 16-bit one
                                    (A/B measurements, testing) */
+    VDEC_NO_JIT = 8u            /* polynomials outside the built-in registry: do not compile a specialised kernel at
+                                   run time (NVRTC), run the table-driven kernels (also: environment VDEC_JIT=0) */
 };
 
 /* Mirrors the fields of `struct code_param` the decoders read (common/include/code.h:9-19),
@@ -89,6 +91,12 @@ const char* vdec_last_error(void);
 /* host-only helpers (no device needed): the label table / kernel family a config would get */
 int         vdec_config_labels(const struct vdec_config* cfg, uint8_t* labels /* [2^(K-1)][2] */);
 const char* vdec_config_kernel_name(const struct vdec_config* cfg);
+
+/* Polynomials outside the built-in registry get a kernel specialised at run time (NVRTC; 2-10 s on the first
+ * vdec_create for a code, cached per process).  This compiles that kernel WITHOUT loading or running it (no
+ * device needed): returns the cubin size, 0 when the config is served without run-time compilation, -1 on failure
+ * (vdec_last_error() has the compiler log). */
+long        vdec_jit_check(const struct vdec_config* cfg);
 
 /* geometry */
 uint32_t    vdec_steps(const vdec_t* h);             /* T = L + K - 1 */

@@ -386,3 +386,49 @@ def test_sliding_window_stream_equals_full_length_decoding(cc, orc, torch_cuda, 
     got = dec.decode_stream(xd, 1024, 512, start_known=False).cpu().numpy()
     assert np.array_equal(got[64:], exp[64:])
     dec.close(); d2.close()
+
+
+JIT_CASES = [  # (n, K, L, octal polynomials, frames): polynomials outside every built-in registry
+    (2, 7, 1024, ("165", "127"), 70), (2, 7, 33, ("135", "147"), 33), (2, 6, 200, ("65", "57"), 65), (2, 5, 40, ("23", "35"), 100),
+    (2, 3, 40, ("7", "5"), 200), (3, 7, 300, ("171", "165", "133"), 40), (3, 4, 64, ("13", "15", "17"), 50),
+    (2, 8, 200, ("345", "237"), 37), (2, 9, 301, ("657", "435"), 21), (2, 10, 100, ("1755", "1363"), 9), (2, 12, 64, ("7173", "5261"), 5),
+]
+
+
+@pytest.mark.parametrize("n,K,L,octal,F", JIT_CASES, ids=[f"K{c[1]}n{c[0]}-{'_'.join(c[3])}-L{c[2]}" for c in JIT_CASES])
+@pytest.mark.parametrize("parity", [0, 1], ids=["ref", "linear"])
+def test_run_time_compiled_kernels_vs_oracle(cc, orc, torch_cuda, n, K, L, octal, F, parity):
+    """Any polynomial set decoder_init() accepts (viterbi-decoder.c:168-206) gets a specialised kernel: NVRTC
+    instantiates the register / packed / register-tile templates for it.  Bit-exact against the oracle, and against
+    the table-driven kernels, for soft, hard (16- and 32-bit) and quantised metrics."""
+    from convolutional_codes_b200.codes import CodeParam, left_align
+    code = CodeParam(n, K, L, tuple(left_align(o, K) for o in octal))
+    oc = ocode(code, parity)
+    fam = "regs" if K <= 7 else "tile"
+    _, met = make_soft_inputs(orc, oc, F, 0.5, seed=K * 1000 + L)
+    exp = orc.decode_soft(oc, met)
+    out, name = _decode_soft(cc, torch_cuda, code, parity, met)
+    assert name.startswith(fam + "_soft_f32<") and name.endswith("nvrtc>"), name
+    assert np.array_equal(out, exp), f"{name}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
+    out2, name2 = _decode_soft(cc, torch_cuda, code, parity, met, flags=cc.NO_JIT)
+    assert name2.startswith("generic") and np.array_equal(out2, exp), name2
+    # hard decisions, both register widths
+    _, sym = make_hard_inputs(orc, oc, F, 0.06, seed=K + L)
+    exph, exppm = orc.decode_hard(oc, sym)
+    outh, pmh, nameh = _decode_hard(cc, torch_cuda, code, parity, sym)
+    assert nameh.startswith(fam + "2_hard_u16x2<") and nameh.endswith("nvrtc>"), nameh
+    assert np.array_equal(outh, exph) and np.array_equal(pmh, exppm), nameh
+    if K <= 7:
+        out3, pm3, name3 = _decode_hard(cc, torch_cuda, code, parity, sym, flags=cc.PREFER_32BIT)
+        assert name3.startswith("regs_hard_u16<") and name3.endswith("nvrtc>"), name3
+        assert np.array_equal(out3, exph) and np.array_equal(pm3, exppm), name3
+    # quantised soft metrics (rate 1/2): integer branch metrics 0..7, exact in the reference's float arithmetic
+    if n == 2:
+        q = np.minimum(np.round(met * 2.0), 7).astype(np.uint8)
+        expq = orc.decode_soft(oc, q.astype(np.float32))
+        dec = cc.BatchDecoder(code, cc.SOFT_U8, parity, metric_max=7)
+        outq = dec.decode(torch_cuda.from_numpy(q).cuda()).cpu().numpy()
+        nameq = dec.kernel_name
+        dec.close()
+        assert nameq.startswith(fam + "2_soft_u8x2<") and nameq.endswith("nvrtc>"), nameq
+        assert np.array_equal(outq, expq), nameq

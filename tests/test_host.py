@@ -35,7 +35,9 @@ def test_kernel_selection(cc):
     assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_REF, cc.FORCE_GENERIC).startswith("generic_soft_f32")
     # K = 8 .. 12: lane-group register kernel for linear labels, table-driven for the reference's quirk labels
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("tile_soft_f32<K9 (561,753) ref")
-    assert cc.config_kernel_name(cc.codes.K10_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("generic_soft_f32<K10")
+    # no built-in instantiation: compiled at run time for the polynomials (NVRTC), table-driven only on request
+    assert cc.config_kernel_name(cc.codes.K10_R12, cc.SOFT_F32, cc.PARITY_REF) == "tile_soft_f32<K10 (1167,1545) ref-labels, nvrtc>"
+    assert cc.config_kernel_name(cc.codes.K10_R12, cc.SOFT_F32, cc.PARITY_REF, cc.NO_JIT).startswith("generic_soft_f32<K10")
     assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K8")
     assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_REF).startswith("tile_soft_f32<K8 (371,247) ref")
     assert cc.config_kernel_name(cc.codes.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR, cc.PREFER_LANEGROUP).startswith("regsw_soft_f32<K8")
@@ -56,7 +58,8 @@ def test_kernel_selection(cc):
     assert cc.config_kernel_name(cc.codes.K8_R12, cc.HARD_U16, cc.PARITY_REF).startswith("tile2_hard_u16x2<K8 (371,247) ref")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.HARD_U16, cc.PARITY_LINEAR).startswith("tile2_hard_u16x2<K9")
     assert cc.config_kernel_name(cc.codes.K15_R12, cc.HARD_U16, cc.PARITY_LINEAR).startswith("tile2_hard_u16x2<K15")
-    assert cc.config_kernel_name(cc.codes.K15_R12, cc.HARD_U16, cc.PARITY_REF).startswith("generic_hard_u16<K15")
+    assert cc.config_kernel_name(cc.codes.K15_R12, cc.HARD_U16, cc.PARITY_REF) == "tile2_hard_u16x2<K15 (46321,51271) ref-labels, nvrtc>"
+    assert cc.config_kernel_name(cc.codes.K15_R12, cc.HARD_U16, cc.PARITY_REF, cc.NO_JIT).startswith("generic_hard_u16<K15")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_U8, cc.PARITY_LINEAR, metric_max=7).startswith("tile2_soft_u8x2<K9")
     assert cc.config_kernel_name(cc.codes.K9_R12, cc.SOFT_U8, cc.PARITY_LINEAR, metric_max=255).startswith("generic_soft_u8<K9")
     # quantised soft mode: packed kernel if the caller bounds the metrics, table-driven otherwise
@@ -64,6 +67,27 @@ def test_kernel_selection(cc):
     assert cc.config_kernel_name(k7, cc.SOFT_U8).startswith("generic_soft_u8")
     # codebook 0 has no D^3 tap: the ref-label kernel also serves the linear request
     assert cc.config_kernel_name(cc.get_code(0), cc.SOFT_F32, cc.PARITY_LINEAR).startswith("regs_soft_f32<codebook0")
+
+
+def test_unregistered_polynomials_compile_at_run_time(cc):
+    """NVRTC needs no GPU: the four kernel families instantiate for polynomials outside the registries"""
+    from convolutional_codes_b200.codes import CodeParam, left_align
+    k7 = CodeParam(2, 7, 300, (left_align("165", 7), left_align("127", 7)))
+    k6r3 = CodeParam(3, 6, 100, (left_align("47", 6), left_align("53", 6), left_align("75", 6)))
+    k9 = CodeParam(2, 9, 200, (left_align("657", 9), left_align("435", 9)))
+    assert cc.config_kernel_name(k7, cc.SOFT_F32, cc.PARITY_LINEAR) == "regs_soft_f32<K7 (165,127) linear, nvrtc>"
+    assert cc.config_kernel_name(k7, cc.HARD_U16, cc.PARITY_REF) == "regs2_hard_u16x2<K7 (165,127) ref-labels, nvrtc>"
+    assert cc.config_kernel_name(k7, cc.HARD_U16, cc.PARITY_REF, cc.PREFER_32BIT) == "regs_hard_u16<K7 (165,127) ref-labels, nvrtc>"
+    assert cc.config_kernel_name(k9, cc.SOFT_U8, cc.PARITY_LINEAR, metric_max=3) == "tile2_soft_u8x2<K9 (657,435) linear, nvrtc>"
+    assert cc.config_kernel_name(k9, cc.SOFT_F32, cc.PARITY_LINEAR, cc.FORCE_GENERIC).startswith("generic_soft_f32")
+    assert cc.jit_check(cc.codes.K7_R12, cc.SOFT_F32, cc.PARITY_REF) == 0           # built in: nothing to compile
+    assert cc.jit_check(k7, cc.SOFT_F32, cc.PARITY_LINEAR, cc.NO_JIT) == 0
+    assert cc.jit_check(k7, cc.SOFT_F32, cc.PARITY_LINEAR) > 10000                  # a cubin came back
+    assert cc.jit_check(k6r3, cc.HARD_U16, cc.PARITY_LINEAR) > 10000
+    assert cc.jit_check(k9, cc.SOFT_F32, cc.PARITY_REF) > 10000
+    # rate 1/3 on a large trellis: no tile kernel model, stays table-driven
+    k9r3 = CodeParam(3, 9, 100, (left_align("557", 9), left_align("663", 9), left_align("711", 9)))
+    assert cc.config_kernel_name(k9r3, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("generic_soft_f32<K9 n3")
 
 
 def _declared_functions(header):

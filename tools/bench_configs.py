@@ -34,6 +34,11 @@ def main():
         ("f3 quant K7 r1/2 L1024 (u8 metrics <= 7)", C.K7_R12, cc.SOFT_U8, cc.PARITY_LINEAR, 1000000 // q, 0),
         ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, 511488 // q, 0),
         ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, 511488 // q, 0),
+        # polynomials outside the registries: the same kernel families, compiled at run time by NVRTC (vdec_jit.cu)
+        ("K7 (165,127) soft L1024, nvrtc", cc.CodeParam(2, 7, 1024, (C.left_align("165", 7), C.left_align("127", 7))), cc.SOFT_F32, cc.PARITY_LINEAR, 1000000 // q, 0),
+        ("K7 (165,127) soft L1024, table-driven", cc.CodeParam(2, 7, 1024, (C.left_align("165", 7), C.left_align("127", 7))), cc.SOFT_F32, cc.PARITY_LINEAR, 8192 // q, cc.NO_JIT),
+        ("K7 (165,127) hard L1024, nvrtc", cc.CodeParam(2, 7, 1024, (C.left_align("165", 7), C.left_align("127", 7))), cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, 0),
+        ("K9 (657,435) soft L1024, nvrtc", cc.CodeParam(2, 9, 1024, (C.left_align("657", 9), C.left_align("435", 9))), cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, 0),
         ("C2 generic K7 (table-driven)", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 8192 // q, cc.FORCE_GENERIC),
         ("K8 soft L1024", C.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 262144 // q, 0),
         ("K8 soft L1024 (lane-group)", C.K8_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 262144 // q, cc.PREFER_LANEGROUP),
