@@ -15,7 +15,8 @@ only = only[0] if only else None
 extra = [a for a in extra if not a.startswith("--only=")]
 out = os.path.join(ROOT, "build", name)
 os.makedirs(out, exist_ok=True)
-flags = ["-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v", *extra]
+flags = ["-std=c++20", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+         "-I", os.path.join(ROOT, "build", "obj"), *extra]          # build/obj holds the generated vdec_jit_sources.inc
 
 
 def comp(n):
@@ -29,7 +30,8 @@ def comp(n):
 
 
 with cf.ThreadPoolExecutor(8) as ex:
-    objs = list(ex.map(comp, ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_tile2.cu", "vdec_generic.cu", "vdec_synth.cu"]))
+    objs = list(ex.map(comp, ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_tile2.cu", "vdec_generic.cu", "vdec_synth.cu",
+                              "vdec_jit.cu"]))
 subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", os.path.join(out, "libvdec.so"), *objs,
-                "-Xlinker", "-Bsymbolic"], check=True)
+                "-Xlinker", "-Bsymbolic", "-ldl"], check=True)
 print("built", out)
