@@ -245,6 +245,31 @@ def run_gpu(args) -> int:
     e2e_iq_gbit = world * Fe * code.L * e2e_steps / float(tq.item()) / 1e9
     assert torch.equal(host_out.to(dev), out[:Fe]), "raw-I/Q path and metric path disagree"
 
+    # ---- the hard-decision decoder end to end (binary-symmetric-channel/viterbi-decoder.c: one symbol byte per step):
+    #      1030 B in, 129 B out per frame, so PCIe carries 8 x fewer bytes per decoded bit than the float metrics
+    hdec = cc.BatchDecoder(code, cc.HARD_U16, cc.PARITY_REF, device=local)
+    Fh = min(4 * Fe, F)
+    _, hsym = hdec.synth_bsc(Fh, rank * F, SEED, 20000)
+    host_sym = torch.empty((Fh, code.T), dtype=torch.uint8, pin_memory=True)
+    host_sym.copy_(hsym)
+    host_hout = torch.empty((Fh, hdec.out_bytes), dtype=torch.uint8, pin_memory=True)
+    host_hpm = torch.empty((Fh,), dtype=torch.int32, pin_memory=True)
+    for _ in range(2):
+        hdec.decode_host(host_sym, out=host_hout, path_metric=host_hpm)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hdec.decode_host(host_sym, out=host_hout, path_metric=host_hpm)
+    th = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    e2e_hard_gbit = world * Fh * code.L * e2e_steps / float(th.item()) / 1e9
+    hout_dev, _ = hdec.decode(hsym)
+    assert torch.equal(host_hout.to(dev), hout_dev), "hard-decision host path and device path disagree"
+    hard_kernel = hdec.kernel_name
+    del hsym, hout_dev
+    hdec.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -313,6 +338,9 @@ def run_gpu(args) -> int:
                 "frames_per_step": Fe, "api": "vdec_decode_host (pinned host buffers, 2-stream pipeline)"},
         "e2e_iq": {"value": e2e_iq_gbit, "unit": UNIT, "h2d_bytes_per_step": Fe * code.T * 8, "d2h_bytes_per_step": Fe * dec.out_bytes,
                    "frames_per_step": Fe, "api": "vdec_decode_iq_host (raw I/Q in, demapper on the GPU; SURVEY 8f-2)"},
+        "e2e_hard": {"value": e2e_hard_gbit, "unit": UNIT, "h2d_bytes_per_step": Fh * code.T, "d2h_bytes_per_step": Fh * (dec.out_bytes + 4),
+                     "frames_per_step": Fh, "kernel": hard_kernel,
+                     "api": "vdec_decode_host, VDEC_HARD_U16 (the BSC decoder's input: one symbol byte per step), same code and frame length"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "acs_gstate_updates_per_s": world * state_updates / 1e9,
