@@ -9,7 +9,8 @@
 // instruction updates two frames.  Per butterfly (2 states x 2 frames = 4 state updates), 8 issue slots:
 //     2 x add            ce = pe + bm[even label]              (halves never carry: every metric < 2^15)
 //     2 x VIADDMNMX.U16x2  new = min(po + bm[odd label], ce)   (sm_90+ DPX: add and packed min in one slot)
-//     2 x IADD3          t  = ce - po + (0x7FFF7FFF - bm[odd]) = ce - co + 0x7FFF per half: bit 15 of each
+//     2 x IADD3          t  = ce - po + (0x7FFF7FFF - bm[odd]) = ce - co + 0x7FFF per half (for S >= 16 formed as
+//                        (pe - po) + table[label pair] with three FMA-pipe adds, see acs_step2): bit 15 of each
 //                        half is set iff co < ce, i.e. the reference's strict '<' decision (tie -> even
 //                        predecessor, viterbi-decoder.c:122), with no borrow between the halves
 //     1 x PRMT           sign-replicates the four decision bytes of (t0, t1) into 0x00 / 0xFF bytes
@@ -64,14 +65,62 @@ __device__ __forceinline__ void packed_bm(uint2 x, uint32_t (&bm)[M]) {
     }
 }
 
+#ifndef VDEC_REGS2_SPLIT
+#define VDEC_REGS2_SPLIT 1
+#endif
+// a - b that ptxas does not merge with a following add into one 3-input IADD3
+__device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t add_opaque(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// a + b written as a * 1 + b: ptxas keeps it an IMAD (FMA pipes) instead of an ALU-pipe IADD3
+__device__ __forceinline__ uint32_t mad1(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// does any butterfly of the code compare label pair I = (even label) * M + (odd label)?  (the same set at every phase)
+template <class CD>
+VDEC_HD constexpr bool label_pair_used(int I) {
+    for (uint32_t u = 0; u < (uint32_t)CD::S; u += 2)
+        for (uint32_t i = 0; i < 2; ++i)
+            if ((int)(CD::label(u, i) * CD::M + CD::label(u + 1, i)) == I) return true;
+    return false;
+}
+
 template <int S> struct Surv2 { static constexpr int NW = (S + 15) / 16; };   // 8 butterflies x 2 states x 2 frames per word
 
 template <class CD, int PH>
 __device__ __forceinline__ void acs_step2(uint32_t (&r)[CD::S], const uint32_t (&bm)[CD::M], uint32_t (&dw)[Surv2<CD::S>::NW]) {
     constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M;
-    uint32_t kb[M];
+    // Two forms of the decision word t (bit 15 of each half = strict '<'), equal modulo 2^32:
+    //   fused  t = ce - po + kb[odd label]                    one 3-input IADD3 per successor: ALU pipe only
+    //   split  t = (pe - po) + cc[even label][odd label]      the difference is shared by both successors and the
+    //          constants cc = bm[even] - bm[odd] + 0x7FFF (per half) by all butterflies with that label pair: three
+    //          2-input adds per butterfly, written as IMAD so that they go to the FMA pipes.
+    // The kernel is bound by the half-rate ALU pipe (6 of its 8 slots per butterfly); the split form leaves 4 there
+    // (measured K = 7 hard 131.7 -> 137.2 Gbit/s, quantised 128.0 -> 132.0, K = 15 hard 0.530 -> 0.553).  With few
+    // butterflies per step the per-step table costs more than it saves (K = 3: 629 -> 594), hence S >= 16.
+    constexpr bool kSplit = VDEC_REGS2_SPLIT && S >= 16;
+    [[maybe_unused]] uint32_t cc[M * M];
+    [[maybe_unused]] uint32_t kb[M];
+    if constexpr (kSplit) {
+        static_for<0, M * M>([&](auto ic) {
+            constexpr int I = decltype(ic)::value;
+            if constexpr (label_pair_used<CD>(I)) cc[I] = add_opaque(bm[I / M], kBias2 - bm[I % M]);
+            else cc[I] = 0;
+        });
+    } else {
 #pragma unroll
-    for (int e = 0; e < M; ++e) kb[e] = kBias2 - bm[e];
+        for (int e = 0; e < M; ++e) kb[e] = kBias2 - bm[e];
+    }
 #pragma unroll
     for (int w = 0; w < Surv2<S>::NW; ++w) dw[w] = 0;
     static_for<0, S>([&](auto ac) {
@@ -81,8 +130,15 @@ __device__ __forceinline__ void acs_step2(uint32_t (&r)[CD::S], const uint32_t (
             constexpr uint32_t u = rotr_bits(a, PH, B), v = u + 1, m = u >> 1;     // new states m (input 0) and m + S/2 (input 1)
             const uint32_t pe = r[a], po = r[b];
             const uint32_t ce0 = pe + bm[CD::label(u, 0)], ce1 = pe + bm[CD::label(u, 1)];
-            const uint32_t t0 = ce0 - po + kb[CD::label(v, 0)];
-            const uint32_t t1 = ce1 - po + kb[CD::label(v, 1)];
+            uint32_t t0, t1;
+            if constexpr (kSplit) {
+                const uint32_t dd = sub_opaque(pe, po);
+                t0 = mad1(dd, cc[CD::label(u, 0) * M + CD::label(v, 0)]);
+                t1 = mad1(dd, cc[CD::label(u, 1) * M + CD::label(v, 1)]);
+            } else {
+                t0 = ce0 - po + kb[CD::label(v, 0)];
+                t1 = ce1 - po + kb[CD::label(v, 1)];
+            }
             r[a] = __viaddmin_u16x2(po, bm[CD::label(v, 0)], ce0);
             r[b] = __viaddmin_u16x2(po, bm[CD::label(v, 1)], ce1);
             uint32_t p;
@@ -159,7 +215,7 @@ vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t
         constexpr int PH = decltype(phc)::value;
         if (PH < (int)rem) {
             const uint2 x = xn;
-            xn = fetch(min(t + PH + 1, T - 1));
+            xn = fetch(min(t + PH + 1, T - 1));                                // one step of lookahead
             packed_bm<M, MODE>(x, bm);
             acs_step2<CD, PH>(r, bm, dw);
             store_dw(t + PH);
