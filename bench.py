@@ -290,7 +290,7 @@ def run_gpu(args) -> int:
     state_updates = F * code.T * code.S / (ms_step * 1e-3)              # per GPU
     f_clk = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
     alu = {"unit": "state-updates/s", "achieved": state_updates,
-           "issue_peak_at_max_clock": sms * 4 * 32 * sm_max_mhz * 1e6 / 4.0,       # 4 issue slots per update
+           "issue_peak_at_max_clock": sms * 4 * 32 * sm_max_mhz * 1e6 / 4.0,       # 4 issue slots per update (FADD2, compare, min, decision; 3.1 measured since the sign-based decisions)
            "alu_pipe_peak_at_max_clock": sms * 32 * sm_max_mhz * 1e6 / 1.0,        # 2 half-rate ALU-pipe ops per update
            "frac_of_issue_peak_at_observed_clock": state_updates / (sms * 4 * 32 * f_clk / 4.0)}
 

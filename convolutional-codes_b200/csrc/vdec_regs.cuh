@@ -46,6 +46,7 @@ struct CodeDef {
     // builds): labellings with fewer shared candidate sums, and n = 3, spill at 128 registers and run
     // 5 % faster with 168 registers and 3 CTAs; the reference-labelled (171,133) code prefers 4.
     static constexpr int kMinBlocks = (K_ == 7 && !(N_ == 2 && REF_)) ? 3 : VDEC_MINB_REF;
+    static constexpr bool kSignDecisions = (N_ == 2 && REF_);      // survivor bits from packed differences, see kDecSign
     VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {
         const uint64_t p[3] = {P0_, P1_, P2_};
         return branch_label(K_, N_, p, REF_, s, i);
@@ -238,9 +239,85 @@ VDEC_HD constexpr bool pair_used(int I) {
     return false;
 }
 
+// ---- decisions from the SIGN of packed differences (64-state steps) ---------------------------------------------------
+// At every phase but 0 the two lanes of a candidate pair are the even (resp. odd) candidates of TWO new states, so one
+// more FADD2 gives both differences co - ce, whose sign bits ARE the reference's strict '<' decisions: negative iff
+// co < ce; equal candidates give +0 (tie -> even predecessor); INF - INF gives the positive canonical NaN (both
+// unreachable -> 0, as `INF < INF` is false).  One PRMT copies the two sign bits, replicated over a byte each, into
+// two byte lanes of a word and one LOP3 ORs the selected bit of each lane into the survivor word: 1.5 issue slots per
+// decision pair-half instead of FSETP + predicated FADD (2.0), and no float-to-word conversion at the end of the step.
+// Layout: the decision of new state j at rotation phase ph is bit dec_pos(j, ph) = rotl6(j, (ph + 4) % 6) of the
+// step's 64-bit vector — the rotation puts the one bit in which the two states of a pair differ at position 3, i.e.
+// into the byte-lane index, for every phase (phase 0 pairs j with j + 32).  The traceback applies the same rotation.
+#ifndef VDEC_DEC_SIGN
+#define VDEC_DEC_SIGN 1
+#endif
+// Measured (gpurun_out/configs_s3n.jsonl vs configs_s3m.jsonl): K = 7 (171,133) reference labels 107.3 -> 110.0 Gbit/s
+// (1503 -> 1181 instructions per 6 steps), tile kernels K = 9 +3 %, K = 15 +2 %; the linear K = 7 code (-1.6 %) and
+// rate 1/3 (-5 %) lose, so a code opts in through kSignDecisions.
+template <class CD> constexpr bool kDecSign = VDEC_DEC_SIGN && CD::B == 6 && CD::S == 64 && CD::kSignDecisions;
+VDEC_HD constexpr uint32_t dec_rot(int ph) { return (uint32_t)((ph % 6 + 4) % 6); }
+VDEC_HD constexpr uint32_t dec_pos(uint32_t j, int ph) { return rotl_bits(j, dec_rot(ph), 6); }
+
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+    uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+// survivor bits PA and PB_ (same word, different byte lanes) <- sign bits of da and db
+template <uint32_t PA, uint32_t PB_>
+__device__ __forceinline__ void put_signs(uint32_t (&dw)[2], float da, float db) {
+    static_assert((PA >> 5) == (PB_ >> 5) && ((PA >> 3) & 3u) != ((PB_ >> 3) & 3u), "one word, two byte lanes");
+    constexpr uint32_t la = (PA >> 3) & 3u, lb = (PB_ >> 3) & 3u;
+    constexpr uint32_t sel = (0xBu << (4 * la)) | (0xFu << (4 * lb));       // byte 3 of da / of db, sign-replicated
+    constexpr uint32_t mask = (1u << (PA & 31u)) | (1u << (PB_ & 31u));
+    uint32_t p;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(p) : "r"(__float_as_uint(da)), "r"(__float_as_uint(db)), "n"(sel));
+    dw[PA >> 5] |= p & mask;
+}
+__device__ __forceinline__ float min_f32(float a, float b) {
+    float r; asm("min.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+}
+
 template <class CD, int PH>
 __device__ __forceinline__ void acs_step_f2(uint64_t (&rp)[CD::S / 2], const uint64_t (&bp)[CD::M * CD::M], uint32_t (&dw)[CD::NW]) {
     constexpr int B = CD::B, S = CD::S, PB = PH % B, M = CD::M, NA = (S + kAccBits - 1) / kAccBits;
+    if constexpr (kDecSign<CD>) {
+        dw[0] = 0; dw[1] = 0;
+        if constexpr (PB == 0) {
+            static_for<0, S / 2>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                constexpr uint32_t u = rotr_bits(2 * q, PH, B), v = u + 1;
+                constexpr uint32_t j0 = u >> 1, j1 = j0 + S / 2;
+                float e0, o0, e1, o1;
+                unpack2(fadd2(rp[q], bp[CD::label(u, 0) * M + CD::label(v, 0)]), e0, o0);
+                unpack2(fadd2(rp[q], bp[CD::label(u, 1) * M + CD::label(v, 1)]), e1, o1);
+                put_signs<dec_pos(j0, PH), dec_pos(j1, PH)>(dw, __fsub_rn(o0, e0), __fsub_rn(o1, e1));
+                rp[q] = pack2(min_f32(e0, o0), min_f32(e1, o1));
+            });
+        } else {
+            static_for<0, S / 2>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                if constexpr (((q >> (PB - 1)) & 1) == 0) {
+                    constexpr int q2 = q | (1 << (PB - 1));
+                    constexpr uint32_t u0 = rotr_bits(2 * q, PH, B), u1 = rotr_bits(2 * q + 1, PH, B);
+                    constexpr uint32_t v0 = u0 + 1, v1 = u1 + 1;
+                    constexpr uint32_t ja = u0 >> 1, jb = u1 >> 1;          // input-0 successors; +S/2 for input 1
+                    const uint64_t e = fadd2(rp[q],  bp[CD::label(u0, 0) * M + CD::label(u1, 0)]);
+                    const uint64_t o = fadd2(rp[q2], bp[CD::label(v0, 0) * M + CD::label(v1, 0)]);
+                    const uint64_t f = fadd2(rp[q],  bp[CD::label(u0, 1) * M + CD::label(u1, 1)]);
+                    const uint64_t p = fadd2(rp[q2], bp[CD::label(v0, 1) * M + CD::label(v1, 1)]);
+                    float ea, eb, oa, ob, fa, fb, pa, pb_, da0, db0, da1, db1;
+                    unpack2(e, ea, eb); unpack2(o, oa, ob); unpack2(f, fa, fb); unpack2(p, pa, pb_);
+                    unpack2(fsub2(o, e), da0, db0);
+                    unpack2(fsub2(p, f), da1, db1);
+                    put_signs<dec_pos(ja, PH), dec_pos(jb, PH)>(dw, da0, db0);
+                    put_signs<dec_pos(ja + S / 2, PH), dec_pos(jb + S / 2, PH)>(dw, da1, db1);
+                    rp[q] = pack2(min_f32(ea, oa), min_f32(eb, ob));
+                    rp[q2] = pack2(min_f32(fa, pa), min_f32(fb, pb_));
+                }
+            });
+        }
+        return;
+    }
     float da[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) da[a] = 0.f;
@@ -558,7 +635,7 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
         load(wb, base - kTraceChunk);
         l2_prefetch(base - 2 * kTraceChunk);
         l2_prefetch(base - 3 * kTraceChunk);
-        if constexpr (NW == 2) {                  // the last 6 steps take their word-select bit from the final state itself
+        if constexpr (NW == 2 && !(MP::kPacked && kDecSign<CD>)) {   // the last 6 steps take their word-select bit from the final state itself
 #pragma unroll
             for (int j = 0; j < kTraceChunk; ++j) {
                 const int ia = jmax - j, ib = jmax + kTraceChunk - j;       // steps back from T-1
@@ -566,12 +643,28 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
                 if (ib <= 5) sb[j] = ((cur >> (5 - ib)) & 1u) ? wb[j].y : wb[j].x;
             }
         }
+        // sign-based decisions (acs_step_f2): the bit of state cur at step tt is rotl6(cur, (tt + 4) % 6) = rotr6(cur, s6)
+        [[maybe_unused]] uint32_t s6 = (6u - (T + 3u) % 6u) % 6u;                  // for tt = T - 1, then + 1 (mod 6) per step back
+        constexpr bool kSignLayout = MP::kPacked && kDecSign<CD>;
         auto walk = [&](SW (&cw)[kTraceChunk], uint32_t (&cs)[kTraceChunk], SW (&nw)[kTraceChunk], uint32_t (&ns)[kTraceChunk], auto guard) {
             constexpr bool GUARD = decltype(guard)::value;      // first chunk only: steps >= T do not exist
 #pragma unroll
             for (int j = kTraceChunk - 1; j >= 0; --j) {
                 const int tt = base + j;
                 if (GUARD && j > jmax) continue;
+                if constexpr (kSignLayout) {
+                    if ((j & 15) == 0) {
+                        const uint32_t rv = __brev(h >> (B - 1));
+                        srow[tt >> 3] = (unsigned char)(rv >> 24);
+                        if (!GUARD || tt + 8 < (int)T) srow[(tt >> 3) + 1] = (unsigned char)(rv >> 16);
+                    }
+                    const uint32_t cur = h & 63u;
+                    const uint32_t jp = ((cur * 65u) >> s6) & 63u;                  // rotr6(cur, s6)
+                    const uint32_t word = (jp & 32u) ? cw[j].y : cw[j].x;
+                    h = (h << 1) | ((word >> (jp & 31u)) & 1u);                     // predecessor (:86)
+                    s6 = (s6 == 5u) ? 0u : s6 + 1u;
+                    continue;
+                }
                 if ((j & 15) == 0) {                             // bits tt .. tt+15 -> bytes tt/8, tt/8+1, MSB-first (:88)
                     const uint32_t rv = __brev(h >> (B - 1));
                     srow[tt >> 3] = (unsigned char)(rv >> 24);

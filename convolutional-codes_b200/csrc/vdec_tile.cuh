@@ -157,6 +157,7 @@ struct TileDef {
 template <class TD, int KS>
 struct TileCode {
     static constexpr int K = 7, N = 2, B = 6, S = 64, M = TD::ML, NW = 2;
+    static constexpr bool kSignDecisions = true;                               // the traceback kernel assumes this layout
     VDEC_HD static constexpr uint32_t label(uint32_t u, uint32_t i) {          // register part of the (extended) label
         uint32_t x = i ? TD::gin() : 0u;
         for (int c = 0; c < 6; ++c)
@@ -390,7 +391,10 @@ vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ 
                 if (tt + 8 < (int)T) row[(tt >> 3) + 1] = (uint8_t)(rv >> 16);
             }
             const uint32_t cur = h & S1;
-            const uint32_t bit = (cur & ((1u << (5 - k)) - 1u)) | ((cur >> (B - 1 - k)) << (5 - k));
+            uint32_t bit = (cur & ((1u << (5 - k)) - 1u)) | ((cur >> (B - 1 - k)) << (5 - k));
+#if VDEC_DEC_SIGN
+            bit = rotl_bits(bit, dec_rot(k), 6);                         // survivor bit layout of acs_step_f2 (vdec_regs.cuh)
+#endif
             const uint32_t word = (bit & 32u) ? wd[k].y : wd[k].x;
             h = (h << 1) | ((word >> (bit & 31u)) & 1u);                 // predecessor (:86)
         }
