@@ -643,11 +643,17 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
                 if (ib <= 5) sb[j] = ((cur >> (5 - ib)) & 1u) ? wb[j].y : wb[j].x;
             }
         }
-        // sign-based decisions (acs_step_f2): the bit of state cur at step tt is rotl6(cur, (tt + 4) % 6) = rotr6(cur, s6)
-        [[maybe_unused]] uint32_t s6 = (6u - (T + 3u) % 6u) % 6u;                  // for tt = T - 1, then + 1 (mod 6) per step back
+        // Sign-based decisions (acs_step_f2): the bit of state cur at step tt is jp = rotl6(cur, (tt + 4) % 6).  One step
+        // back the state becomes (cur << 1 | d) & 63 and the rotation one less, which leaves every bit of jp where it is
+        // except bit (tt + 3) % 6, which takes the decision d: the index is kept incrementally with one bit insert per
+        // step.  The bit position is a compile-time constant when the phase of a chunk is: chunks are 16 steps, phases
+        // have period 6, so the walk is instantiated for the three residues of (chunk start / 16) mod 3.
         constexpr bool kSignLayout = MP::kPacked && kDecSign<CD>;
-        auto walk = [&](SW (&cw)[kTraceChunk], uint32_t (&cs)[kTraceChunk], SW (&nw)[kTraceChunk], uint32_t (&ns)[kTraceChunk], auto guard) {
+        [[maybe_unused]] uint32_t jp = (((cur & 63u) * 65u) >> (6u - (T + 3u) % 6u)) & 63u;      // for tt = T - 1
+        auto walk = [&](SW (&cw)[kTraceChunk], uint32_t (&cs)[kTraceChunk], SW (&nw)[kTraceChunk], uint32_t (&ns)[kTraceChunk], auto guard,
+                        auto cls) {
             constexpr bool GUARD = decltype(guard)::value;      // first chunk only: steps >= T do not exist
+            [[maybe_unused]] constexpr int CLS = decltype(cls)::value;
 #pragma unroll
             for (int j = kTraceChunk - 1; j >= 0; --j) {
                 const int tt = base + j;
@@ -658,11 +664,11 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
                         srow[tt >> 3] = (unsigned char)(rv >> 24);
                         if (!GUARD || tt + 8 < (int)T) srow[(tt >> 3) + 1] = (unsigned char)(rv >> 16);
                     }
-                    const uint32_t cur = h & 63u;
-                    const uint32_t jp = ((cur * 65u) >> s6) & 63u;                  // rotr6(cur, s6)
+                    const uint32_t bpos = (uint32_t)((16 * CLS + j) % 6 + 3) % 6u;      // (tt + 3) % 6, a constant after unrolling
                     const uint32_t word = (jp & 32u) ? cw[j].y : cw[j].x;
-                    h = (h << 1) | ((word >> (jp & 31u)) & 1u);                     // predecessor (:86)
-                    s6 = (s6 == 5u) ? 0u : s6 + 1u;
+                    const uint32_t x = __funnelshift_r(word, 0u, jp);                   // bit 0: decision of state cur at step tt
+                    h = (h << 1) | (x & 1u);                                            // predecessor (:86)
+                    jp = (jp & ~(1u << bpos)) | ((x << bpos) & (1u << bpos));
                     continue;
                 }
                 if ((j & 15) == 0) {                             // bits tt .. tt+15 -> bytes tt/8, tt/8+1, MSB-first (:88)
@@ -681,18 +687,29 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
                 }
             }
         };
-        walk(wa, sa, wb, sb, std::true_type{});
+        // chunk class = (base / 16) mod 3, warp-uniform; only the sign layout distinguishes the classes
+        auto walk_cls = [&](SW (&cw)[kTraceChunk], uint32_t (&cs)[kTraceChunk], SW (&nw)[kTraceChunk], uint32_t (&ns)[kTraceChunk], auto guard) {
+            if constexpr (!kSignLayout) {
+                walk(cw, cs, nw, ns, guard, std::integral_constant<int, 0>{});
+            } else {
+                const uint32_t cls = ((uint32_t)base >> 4) % 3u;
+                if (cls == 0) walk(cw, cs, nw, ns, guard, std::integral_constant<int, 0>{});
+                else if (cls == 1) walk(cw, cs, nw, ns, guard, std::integral_constant<int, 1>{});
+                else walk(cw, cs, nw, ns, guard, std::integral_constant<int, 2>{});
+            }
+        };
+        walk_cls(wa, sa, wb, sb, std::true_type{});
         for (;;) {
             base -= kTraceChunk;
             if (base < 0) break;
             load(wa, base - kTraceChunk);
             l2_prefetch(base - 4 * kTraceChunk);
-            walk(wb, sb, wa, sa, std::false_type{});
+            walk_cls(wb, sb, wa, sa, std::false_type{});
             base -= kTraceChunk;
             if (base < 0) break;
             load(wb, base - kTraceChunk);
             l2_prefetch(base - 4 * kTraceChunk);
-            walk(wa, sa, wb, sb, std::false_type{});
+            walk_cls(wa, sa, wb, sb, std::false_type{});
         }
     }
     __syncwarp();
