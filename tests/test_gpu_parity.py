@@ -432,3 +432,19 @@ def test_run_time_compiled_kernels_vs_oracle(cc, orc, torch_cuda, n, K, L, octal
         dec.close()
         assert nameq.startswith(fam + "2_soft_u8x2<") and nameq.endswith("nvrtc>"), nameq
         assert np.array_equal(outq, expq), nameq
+
+
+@pytest.mark.parametrize("key,parity", [("k7r12", 0), ("k7r12", 1), ("k9", 0), ("k9", 1), ("k8", 0)],
+                         ids=["k7-ref", "k7-linear", "k9-ref", "k9-linear", "k8-ref"])
+def test_every_frame_length_residue(cc, orc, torch_cuda, key, parity):
+    """The survivor-bit layout of the sign-based decisions rotates with the step index (period 6) and the register
+    kernel's traceback walks 16-step chunks in three phase classes: every T mod 48 (and every tile-window remainder
+    T mod 6) must decode bit-exactly, including frames shorter than one period."""
+    for L in list(range(1, 56)) + [95, 96, 97, 143, 144, 145]:
+        code = _get(cc, key, L)
+        oc = ocode(code, parity)
+        F = 37 if L < 56 else 9
+        _, met = make_soft_inputs(orc, oc, F, 0.55, seed=7000 + L)
+        exp = orc.decode_soft(oc, met)
+        out, name = _decode_soft(cc, torch_cuda, code, parity, met)
+        assert np.array_equal(out, exp), f"{name} L={L}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
