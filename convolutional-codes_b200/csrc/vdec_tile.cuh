@@ -36,6 +36,19 @@ VDEC_HD constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return
 #ifndef VDEC_TILE_VB
 #define VDEC_TILE_VB 2
 #endif
+// Survivor layout.  Step-major [frame][step][thread] lets the frame's threads store one contiguous record per step, but
+// the traceback needs ONE thread's word per step and fetches a 32-byte sector for it.  Thread-major
+// [frame][thread][step] makes a window's words 48 contiguous bytes for the traceback; the forward stores become 8-byte
+// pieces that L2 merges into sectors.  Measured on the same box (gpurun_out/ab_s3x.log, ab_s3y.log, ab_s3zy.log),
+// thread-major against step-major: K = 8 -5 %, K = 9 +-0, K = 11 +5.8 %, K = 13 +1 %, K = 15 -1.5 %; hence thread-major
+// for 8 .. 64 threads per frame (K = 10 .. 13).
+#ifndef VDEC_TILE_TM_MIN
+#define VDEC_TILE_TM_MIN 8
+#endif
+#ifndef VDEC_TILE_TM_MAX
+#define VDEC_TILE_TM_MAX 64
+#endif
+VDEC_HD constexpr bool tile_thread_major(uint32_t tpf) { return tpf >= VDEC_TILE_TM_MIN && tpf <= VDEC_TILE_TM_MAX; }
 
 template <int K_, uint64_t P0_, uint64_t P1_, bool REF_ = false, int VB_ = (K_ == 8 ? 1 : VDEC_TILE_VB)>
 struct TileDef {
@@ -46,6 +59,8 @@ struct TileDef {
     static_assert(K_ >= 8 && K_ <= 15, "register-tile kernel covers K = 8 .. 15");
     static_assert(K_ > 8 || VB_ <= 1, "K = 8: the reader's second register bit is a register bit of the writer too, so at most 2 registers per LDS");
     static constexpr int FPC = kTileThreads / TPF;            // frames per CTA
+    static constexpr bool kThreadMajor = tile_thread_major(TPF);   // survivor layout, see VDEC_TILE_TM_MIN / _MAX
+    static constexpr bool kSign = K_ >= 9;                    // sign-based decisions (vdec_regs.cuh kDecSign): K = 8 loses 7 % with them
     static constexpr int RT = TPF > 32 ? TPF : 32;            // threads sharing one exchange region
     static constexpr int RTB = ilog2(RT);
     static constexpr int E = 6 + RTB;                         // address bits of a region (RT * 64 floats)
@@ -157,7 +172,7 @@ struct TileDef {
 template <class TD, int KS>
 struct TileCode {
     static constexpr int K = 7, N = 2, B = 6, S = 64, M = TD::ML, NW = 2;
-    static constexpr bool kSignDecisions = true;                               // the traceback kernel assumes this layout
+    static constexpr bool kSignDecisions = TD::kSign;                          // the traceback kernel is told (TileShape::sign)
     VDEC_HD static constexpr uint32_t label(uint32_t u, uint32_t i) {          // register part of the (extended) label
         uint32_t x = i ? TD::gin() : 0u;
         for (int c = 0; c < 6; ++c)
@@ -259,7 +274,7 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
     for (int q = 0; q < 32; ++q) rp[q] = pack2(rest, rest);
     if (tau == 0) rp[0] = pack2(0.f, rest);
 
-    uint2* sv = surv + (size_t)f * T * TPF + tau;
+    uint2* sv = TD::kThreadMajor ? surv + ((size_t)f * TPF + tau) * T : surv + (size_t)f * T * TPF + tau;
     uint32_t t = 0;
     auto begin_window = [&]() {
         prefetch();
@@ -283,7 +298,7 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
         if constexpr (TD::REF) tile_get_pairs<CD, KS, 2 + FSH>(vma + KS * (64 << FSH), xt[KS], bp);
         else tile_get_pairs<CD, KS>(ring + roff + KS * 16, xt[KS], bp);
         acs_step_f2<CD, KS>(rp, bp, dw);
-        if (live) sv[(size_t)(t + KS) * TPF] = make_uint2(dw[0], dw[1]);
+        if (live) sv[TD::kThreadMajor ? (size_t)(t + KS) : (size_t)(t + KS) * TPF] = make_uint2(dw[0], dw[1]);
     };
     // full windows that are followed by another one: straight-line 6 steps, then the transpose
     for (; t + 6 < T; t += 6) {
@@ -365,6 +380,8 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
 // (cur & (2^(5-k) - 1)) | (cur >> (B-1-k)) << (5-k) of thread (cur >> (5-k)) & (TPF-1)'s word; the thread index is
 // the same for every step of a window, so a window's words are fetched together.  Output as in vdec_regs.cuh:
 // the state doubles as a shift register of decoded bits, 16 of which are emitted every 16 steps (:81-89).
+// THREAD_MAJOR: survivor layout [frame][thread][step] (tile_thread_major); SIGN: rotated survivor-bit layout (TileDef::kSign)
+template <bool THREAD_MAJOR, bool SIGN>
 static __global__ void __launch_bounds__(128)
 vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ final_state, uint8_t* __restrict__ out,
                    uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t B, uint32_t TPF) {
@@ -380,7 +397,7 @@ vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ 
         uint2 wd[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k)
-            if (k < n) wd[k] = __ldcg(sv + (size_t)(w0 + k) * TPF + owner);
+            if (k < n) wd[k] = __ldcg(THREAD_MAJOR ? sv + (size_t)owner * T + (w0 + k) : sv + (size_t)(w0 + k) * TPF + owner);
 #pragma unroll
         for (int k = 5; k >= 0; --k) {
             if (k >= n) continue;
@@ -392,9 +409,7 @@ vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ 
             }
             const uint32_t cur = h & S1;
             uint32_t bit = (cur & ((1u << (5 - k)) - 1u)) | ((cur >> (B - 1 - k)) << (5 - k));
-#if VDEC_DEC_SIGN
-            bit = rotl_bits(bit, dec_rot(k), 6);                         // survivor bit layout of acs_step_f2 (vdec_regs.cuh)
-#endif
+            if constexpr (VDEC_DEC_SIGN && SIGN) bit = rotl_bits(bit, dec_rot(k), 6);   // survivor bit layout of acs_step_f2 (vdec_regs.cuh)
             const uint32_t word = (bit & 32u) ? wd[k].y : wd[k].x;
             h = (h << 1) | ((word >> (bit & 31u)) & 1u);                 // predecessor (:86)
         }
@@ -407,10 +422,11 @@ vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ 
 struct TileShape {
     uint32_t B, TPF, FPC;
     bool ref;
+    bool sign;              // survivor bits in the rotated layout of the sign-based decisions (TileDef::kSign)
 };
 inline TileShape tile_shape(uint32_t K, bool ref) {
     const uint32_t tpf = 1u << (K - 7);
-    return TileShape{K - 1, tpf, (uint32_t)kTileThreads / tpf, ref};
+    return TileShape{K - 1, tpf, (uint32_t)kTileThreads / tpf, ref, K >= 9};
 }
 inline size_t tile_surv_bytes_tpf(const LaunchGeom& g, uint32_t tpf) {
     return (size_t)g.nframes * g.T * tpf * sizeof(uint2) + (size_t)g.nframes * sizeof(uint32_t);
@@ -429,7 +445,12 @@ inline int tile_launch_kernel(const void* kern, const TileShape& sh, const Launc
     uint32_t nframes = g.nframes, T = g.T, stride = g.stride_steps, init_all_from = g.init_all_from;
     void* args[] = {&inf, &surv, &final_state, &nframes, &T, &stride, &init_all_from};
     VDEC_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kTileThreads), args, smem, st));
-    vit_tile_traceback<<<(g.nframes + 127) / 128, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
+    const uint32_t tb_blocks = (g.nframes + 127) / 128;
+    const bool tm = tile_thread_major(sh.TPF);
+    if (tm && sh.sign) vit_tile_traceback<true, true><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
+    else if (tm) vit_tile_traceback<true, false><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
+    else if (sh.sign) vit_tile_traceback<false, true><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
+    else vit_tile_traceback<false, false><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -440,7 +461,7 @@ size_t tile_surv_bytes(const LaunchGeom& g) { return tile_surv_bytes_tpf(g, TD::
 template <class TD>
 int tile_launch(const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st) {
     return tile_launch_kernel(reinterpret_cast<const void*>(&vit_tile_forward<TD>),
-                              TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF}, g, in, out, scratch, st);
+                              TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF, TD::kSign}, g, in, out, scratch, st);
 }
 
 struct TileEntry {

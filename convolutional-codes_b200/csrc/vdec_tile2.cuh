@@ -254,7 +254,7 @@ size_t tile2_surv_bytes(const LaunchGeom& g) { return tile2_surv_bytes_tpf(g, TD
 template <class TD, int MODE>
 int tile2_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* scratch, cudaStream_t st) {
     return tile2_launch_kernel(reinterpret_cast<const void*>(&vit_tile2_forward<TD, MODE>),
-                               TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF}, g, in, out, path_metric,
+                               TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF, false}, g, in, out, path_metric,
                                scratch, st);
 }
 
