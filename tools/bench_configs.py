@@ -52,6 +52,9 @@ def main():
         ("C4 soft K11 L1024", C.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 32768 // q, 0),
         ("C4 soft K9 L1024 (lane-group)", C.K9_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 131072 // q, cc.PREFER_LANEGROUP),
         ("C4 soft K11 L1024 (lane-group)", C.K11_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 32768 // q, cc.PREFER_LANEGROUP),
+        ("K10 soft L1024", C.K10_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 65536 // q, 0),
+        ("K12 soft L1024", C.K12_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 18944 // q, 0),
+        ("K14 soft L1024", C.K14_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 4736 // q, 0),
         ("C4 soft K13 L1024", C.K13_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 9472 // q, 0),
         ("C4 soft K15 L1024", C.K15_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 2368 // q, 0),
         ("C4 soft K15 L1024 ref-labels", C.K15_R12, cc.SOFT_F32, cc.PARITY_REF, 2368 // q, 0),
