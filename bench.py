@@ -153,6 +153,118 @@ def run_reference(args) -> int:
 
 
 # --------------------------------------------------------------------------------------------------
+def set_cpu_affinity(local: int) -> str:
+    """Bind this rank to the CPUs next to its GPU before pinned host memory is first touched (NUMA-local staging)."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return f"nvml ideal cpu set ({len(os.sched_getaffinity(0))} of {before} cpus)"
+    except Exception as e:
+        return "unavailable: " + type(e).__name__
+
+
+def algorithmic_bytes_per_frame(code, metric_kind: str, kernel: str) -> int:
+    """boundary form = input + output per frame; kernels whose survivors live in HBM by design (K >= 8,
+    BASELINE config 4) add the survivor stream: S/8 B per step written, one 32 B sector per step read back."""
+    step = {"soft": code.M * 4, "iq": 8, "hard": 1, "quant": code.M}[metric_kind]
+    b = code.T * step + code.out_bytes + (4 if metric_kind == "hard" else 0)
+    if code.K >= 8:
+        b += code.T * (code.S // 8) + code.T * 32
+    return b
+
+
+def time_decode(torch, fn, reps: int, warm: int = 2) -> float:
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_configs(cc, torch, local: int, alu_peak_ops: float, hbm_peak_gbs: float, quick: int):
+    """Every other BASELINE.json config shape, device-resident, timed in the same run: decoded Gbit/s, ACS
+    Gstate-updates/s and both roofline fractions per entry.  alu_frac counts 4 lane-operations per state update against
+    SMs x 128 lanes x max clock; the packed 16-bit kernels process two lanes per 32-bit lane (ceiling x 2)."""
+    C = cc.codes
+    q = quick
+    cases = [  # id, description, code, metric kind, parity, frames, flags
+        ("C1", "binary-symmetric-simulation: hard K=3 (7,5) codebook 0, L=40, BSC p=0.0125", cc.get_code(0), "hard", cc.PARITY_REF, (1 << 22) // q, 0),
+        ("C2-textbook", "K=7 (171,133) soft, true-parity (textbook) labels, L=1024", C.K7_R12, "soft", cc.PARITY_LINEAR, 500000 // q, 0),
+        ("C2-iq", "K=7 (171,133) soft from raw I/Q (demapper in the kernel's feeder), reference labels", C.K7_R12, "iq", cc.PARITY_REF, 1000000 // q, 0),
+        ("C2-hard", "K=7 (171,133) hard decisions (BSC p=0.02), packed 16-bit", C.K7_R12, "hard", cc.PARITY_REF, 1000000 // q, 0),
+        ("C2-quant", "K=7 (171,133) quantised soft (u8 metrics <= 7), packed 16-bit", C.K7_R12, "quant", cc.PARITY_REF, 1000000 // q, 0),
+        ("C3", "K=7 rate-1/3 (133,171,165) soft, 8-point constellation, L=1024, reference labels", C.K7_R13, "soft", cc.PARITY_REF, 500000 // q, 0),
+        ("C3-textbook", "K=7 rate-1/3 soft, true-parity labels", C.K7_R13, "soft", cc.PARITY_LINEAR, 500000 // q, 0),
+        ("C4-K9", "K=9 (561,753) soft, L=1024, survivors in HBM, true-parity labels", C.K9_R12, "soft", cc.PARITY_LINEAR, 131072 // q, 0),
+        ("C4-K9-ref", "K=9 (561,753) soft, reference labels", C.K9_R12, "soft", cc.PARITY_REF, 131072 // q, 0),
+        ("C4-K15", "K=15 (46321,51271) soft, 16384 states, L=1024, survivors in HBM, true-parity labels", C.K15_R12, "soft", cc.PARITY_LINEAR, 2368 // min(q, 2), 0),
+        ("C4-K15-ref", "K=15 soft, reference labels", C.K15_R12, "soft", cc.PARITY_REF, 2368 // min(q, 2), 0),
+    ]
+    out = []
+    dev = torch.device("cuda", local)
+    for cid, desc, code, kind, parity, F, flags in cases:
+        metric = {"soft": cc.SOFT_F32, "iq": cc.SOFT_F32, "hard": cc.HARD_U16, "quant": cc.SOFT_U8}[kind]
+        dec = cc.BatchDecoder(code, metric, parity, device=local, flags=flags, metric_max=7 if kind == "quant" else 0)
+        if kind == "soft":
+            payload, x = dec.synth_awgn(F, 0, 1, cc.awgn_sigma(EBN0_DB))
+        elif kind == "iq":
+            payload, x = dec.synth_awgn(F, 0, 1, cc.awgn_sigma(EBN0_DB), want_iq=True, want_metrics=False)
+        elif kind == "quant":
+            payload, xf = dec.synth_awgn(F, 0, 1, cc.awgn_sigma(EBN0_DB))
+            x = torch.clamp(torch.round(xf * 2.0), max=7).to(torch.uint8)
+            del xf
+        else:
+            payload, x = dec.synth_bsc(F, 0, 1, 12500 if cid == "C1" else 20000)
+        res = torch.empty((F, dec.out_bytes), dtype=torch.uint8, device=dev)
+        pm = torch.empty((F,), dtype=torch.int32, device=dev)
+        fn = (lambda: dec.decode_iq(x, out=res)) if kind == "iq" else (lambda: dec.decode(x, out=res, path_metric=pm))
+        l0 = dec.launches
+        ms = time_decode(torch, fn, reps=5)
+        launches_per_step = (dec.launches - l0) // 7
+        cnt = dec.count_errors(res, payload).cpu().tolist()
+        kernel = dec.iq_kernel_name if kind == "iq" else dec.kernel_name
+        packed = kernel.startswith(("regs2_", "tile2_"))
+        upd = F * code.T * code.S / (ms * 1e-3)
+        algo = F * algorithmic_bytes_per_frame(code, kind, kernel)
+        alu_frac = upd * 4.0 / (alu_peak_ops * (2.0 if packed else 1.0))
+        hbm_frac = algo / (ms * 1e-3) / 1e9 / hbm_peak_gbs
+        out.append({"id": cid, "workload": desc, "kernel": kernel, "frames": F, "ms": round(ms, 4),
+                    "gbit_s": round(F * code.L / ms / 1e6, 3), "gstate_upd_s": round(upd / 1e9, 1),
+                    "alu_frac": round(alu_frac, 4), "hbm_frac": round(hbm_frac, 4), "bound": "alu" if alu_frac >= hbm_frac else "hbm",
+                    "algorithmic_bytes_per_frame": algo // F, "launches_per_step": launches_per_step,
+                    "ber": cnt[1] / max(cnt[0], 1)})
+        dec.close()
+        del x, res, pm, payload
+        torch.cuda.empty_cache()
+    # sliding-window decoding of one unterminated stream (north_star piece 4, SURVEY 8f-4)
+    code = C.K7_R12
+    dec = cc.BatchDecoder(code, cc.SOFT_F32, cc.PARITY_LINEAR, device=local)
+    nb = ((1 << 28) // q) // code.T
+    _, x = dec.synth_awgn(nb, 0, 1, cc.awgn_sigma(EBN0_DB))
+    x = x.reshape(nb * code.T, code.M)
+    ms = time_decode(torch, lambda: dec.decode_stream(x, 1024, 128, start_known=True), reps=3, warm=1)
+    steps = x.shape[0]
+    upd = (steps / 1024) * 1280 * code.S / (ms * 1e-3)          # every window of 1024 payload steps runs 1280 trellis steps
+    out.append({"id": "stream", "workload": "one unterminated K=7 soft stream of 2^28 steps, windows of 1024 + 2 x 128 steps, stitched",
+                "kernel": dec.kernel_name, "steps": steps, "ms": round(ms, 4), "gbit_s": round(steps / ms / 1e6, 3),
+                "gstate_upd_s": round(upd / 1e9, 1), "alu_frac": round(upd * 4.0 / alu_peak_ops, 4),
+                "hbm_frac": round(steps * 1.25 * 16 / (ms * 1e-3) / 1e9 / hbm_peak_gbs, 4), "bound": "alu"})
+    dec.close()
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args) -> int:
     import numpy as np
     import torch
@@ -165,6 +277,7 @@ def run_gpu(args) -> int:
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (use --impl reference for the CPU arm)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = set_cpu_affinity(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -176,6 +289,7 @@ def run_gpu(args) -> int:
     sigma = cc.awgn_sigma(EBN0_DB)
     payload, metrics = dec.synth_awgn(F, rank * F, SEED, sigma)   # resident in HBM before timing
     out = torch.empty((F, dec.out_bytes), dtype=torch.uint8, device=dev)
+    counters = torch.zeros(3, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
 
     def barrier():
@@ -183,19 +297,38 @@ def run_gpu(args) -> int:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # One step of the sharded simulation (AWGN-channel/main.c:108-141 for a whole batch): decode the rank's frames,
+    # count bit / frame errors against the payload, and sum the three counters over the ranks — the path's ONE
+    # collective (NCCL all-reduce of 24 bytes), inside the timed region.
+    def step():
+        counters.zero_()
+        dec.decode(metrics, out=out)                      # vdec_decode_device on torch's current stream
+        dec.count_errors(out, payload, counters)
+        cc.allreduce_counters(counters)
+
     for _ in range(max(args.warmup, 0)):
-        dec.decode(metrics, out=out)
+        step()
     barrier()
     l0 = dec.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dec_ms = 0.0
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(args.steps):
-            dec.decode(metrics, out=out)                  # vdec_decode_device on torch's current stream
+            step()
         e1.record()
         barrier()
     ms_total = e0.elapsed_time(e1)
     launches = dec.launches - l0
+    # the decoder kernel alone, same buffers, same stream (CUDA events around the launches only): the roofline's kernel time
+    torch.cuda.synchronize()
+    d0.record()
+    for _ in range(args.steps):
+        dec.decode(metrics, out=out)
+    d1.record()
+    torch.cuda.synchronize()
+    dec_ms = d0.elapsed_time(d1) / args.steps
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -203,11 +336,41 @@ def run_gpu(args) -> int:
     ms_step = ms_total / args.steps
     bits = world * F * code.L
     gbit = bits / (ms_step * 1e-3) / 1e9
+    totals = counters.cpu().tolist()                      # all ranks, last step
 
-    # error counters of the last step, summed over ranks: the path's one collective (main.c:129-141,233)
-    counters = dec.count_errors(out, payload)
-    cc.allreduce_counters(counters)
-    counters = counters.cpu().tolist()
+    # ---- GPU-resident link (config 5's inner loop): source -> channel (raw I/Q) -> demapper+decoder -> error count
+    Fl = min(F, 1 << 19)
+    lcount = torch.zeros(3, dtype=torch.int64, device=dev)
+
+    def link_step():
+        pl, iq = dec.synth_awgn(Fl, rank * F, SEED + 1, sigma, want_iq=True, want_metrics=False)
+        o = dec.decode_iq(iq, out=out[:Fl])
+        dec.count_errors(o, pl, lcount)
+
+    link_ms = time_decode(torch, link_step, reps=3, warm=1)
+    tl = torch.tensor([link_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    link_gbit = world * Fl * code.L / (float(tl.item()) * 1e-3) / 1e9
+    iq_kernel = dec.iq_kernel_name
+
+    # ---- bare pinned host -> device bandwidth, all ranks at once: the ceiling of every host-buffer number below
+    hb = torch.empty((256 << 20,), dtype=torch.uint8, pin_memory=True)
+    hb.fill_(1)                                              # first touch on this rank's CPUs
+    db = torch.empty_like(hb, device=dev)
+    db.copy_(hb, non_blocking=True)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(8):
+        db.copy_(hb, non_blocking=True)                     # cudaMemcpyAsync, 256 MiB each
+    h1.record()
+    torch.cuda.synchronize()
+    th2d = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(th2d, op=dist.ReduceOp.MAX)
+    h2d_peak_gbs = world * 8 * hb.numel() / (float(th2d.item()) * 1e-3) / 1e9
+    del hb, db
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H in the timed region
     Fe = min(args.e2e_frames, F)
@@ -226,10 +389,11 @@ def run_gpu(args) -> int:
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_gbit = world * Fe * code.L * e2e_steps / float(te.item()) / 1e9
+    e2e_h2d_gbs = world * Fe * dec.in_bytes * e2e_steps / float(te.item()) / 1e9
     assert torch.equal(host_out.to(dev), out[:Fe]), "host-buffer path and device path disagree"
 
-    # ---- same, through the raw-I/Q entry (demapper fused behind the call: half the PCIe bytes per bit)
-    _, _, iq_dev = dec.synth_awgn(Fe, rank * F, SEED, sigma, want_iq=True)
+    # ---- same, through the raw-I/Q entry (demapper inside the decoder kernel: half the PCIe bytes per bit)
+    _, iq_dev = dec.synth_awgn(Fe, rank * F, SEED, sigma, want_iq=True, want_metrics=False)
     host_iq = torch.empty((Fe, code.T, 2), dtype=torch.float32, pin_memory=True)
     host_iq.copy_(iq_dev)
     del iq_dev
@@ -243,12 +407,13 @@ def run_gpu(args) -> int:
     if world > 1:
         dist.all_reduce(tq, op=dist.ReduceOp.MAX)
     e2e_iq_gbit = world * Fe * code.L * e2e_steps / float(tq.item()) / 1e9
+    e2e_iq_h2d_gbs = world * Fe * code.T * 8 * e2e_steps / float(tq.item()) / 1e9
     assert torch.equal(host_out.to(dev), out[:Fe]), "raw-I/Q path and metric path disagree"
 
     # ---- the hard-decision decoder end to end (binary-symmetric-channel/viterbi-decoder.c: one symbol byte per step):
     #      1030 B in, 129 B out per frame, so PCIe carries 8 x fewer bytes per decoded bit than the float metrics
     hdec = cc.BatchDecoder(code, cc.HARD_U16, cc.PARITY_REF, device=local)
-    Fh = min(4 * Fe, F)
+    Fh = min(8 * Fe, F)
     _, hsym = hdec.synth_bsc(Fh, rank * F, SEED, 20000)
     host_sym = torch.empty((Fh, code.T), dtype=torch.uint8, pin_memory=True)
     host_sym.copy_(hsym)
@@ -264,6 +429,7 @@ def run_gpu(args) -> int:
     if world > 1:
         dist.all_reduce(th, op=dist.ReduceOp.MAX)
     e2e_hard_gbit = world * Fh * code.L * e2e_steps / float(th.item()) / 1e9
+    e2e_hard_h2d_gbs = world * Fh * code.T * e2e_steps / float(th.item()) / 1e9
     hout_dev, _ = hdec.decode(hsym)
     assert torch.equal(host_hout.to(dev), hout_dev), "hard-decision host path and device path disagree"
     hard_kernel = hdec.kernel_name
@@ -275,24 +441,42 @@ def run_gpu(args) -> int:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (one launch per step: the register Viterbi kernel)
+    # ---- roofline of the dominant kernel (one launch per step: the register Viterbi kernel), SURVEY 8d:
+    #      achieved = max(ALU term, HBM term), both reported; ACS is a min-plus recurrence, so the ALU term binds
     hbm_peak, sm_max_mhz, peak_kind = measured_peaks()
-    algo_bytes = F * (code.T * code.M * 4 + dec.out_bytes)              # SURVEY §8d: 16.22 B per decoded bit
-    kern_ms = ms_step * args.steps / max(launches, 1)                    # launches inside the timed region
-    achieved = algo_bytes / (ms_step * 1e-3) / 1e9                       # all launches of a step run the same kernel
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_frame")
-        traffic = traffic * F if traffic is not None else None
     clocks = clk.summary()
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    state_updates = F * code.T * code.S / (ms_step * 1e-3)              # per GPU
-    f_clk = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
-    alu = {"unit": "state-updates/s", "achieved": state_updates,
-           "issue_peak_at_max_clock": sms * 4 * 32 * sm_max_mhz * 1e6 / 4.0,       # 4 issue slots per update (FADD2, compare, min, decision; 3.1 measured since the sign-based decisions)
-           "alu_pipe_peak_at_max_clock": sms * 32 * sm_max_mhz * 1e6 / 1.0,        # 2 half-rate ALU-pipe ops per update
-           "frac_of_issue_peak_at_observed_clock": state_updates / (sms * 4 * 32 * f_clk / 4.0)}
+    alu_peak_ops = sms * 128 * sm_max_mhz * 1e6                          # lane-operations/s at the max SM clock
+    f_obs = (clocks["sm_mhz"] or sm_max_mhz) * 1e6
+    state_updates = F * code.T * code.S / (dec_ms * 1e-3)               # per GPU, decoder kernel alone
+    algo_bytes = F * (code.T * code.M * 4 + dec.out_bytes)              # SURVEY 8d: 16.22 B per decoded bit
+    alu_frac = state_updates * 4.0 / alu_peak_ops
+    hbm_gbs = algo_bytes / (dec_ms * 1e-3) / 1e9
+    hbm_frac = hbm_gbs / hbm_peak
+    traffic, traffic_source = None, None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("dram_bytes_per_frame") is not None:
+            traffic = tj["dram_bytes_per_frame"] * F
+            traffic_source = ("STORED ncu figure, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per frame from "
+                              + str(tj.get("source", "profiles/ncu_traffic.json")) + ", times the frames of one launch")
+    bound = "alu" if alu_frac >= hbm_frac else "hbm"
+    roofline = {
+        "bound": bound,
+        "achieved": state_updates * 4.0 / 1e12 if bound == "alu" else hbm_gbs,
+        "peak": alu_peak_ops / 1e12 if bound == "alu" else hbm_peak,
+        "unit": "Tlane-op/s (4 lane-operations per ACS state update: add, add, compare, select)" if bound == "alu" else "GB/s",
+        "frac": max(alu_frac, hbm_frac),
+        "alu_frac": alu_frac, "alu_frac_at_observed_clock": state_updates * 4.0 / (sms * 128 * f_obs),
+        "alu_achieved_state_updates_per_s": state_updates, "alu_peak_state_updates_per_s": alu_peak_ops / 4.0,
+        "alu_peak_source": f"{sms} SMs x 128 lanes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz, {peak_kind})",
+        "hbm_frac": hbm_frac, "hbm_achieved_gbs": hbm_gbs, "hbm_peak_gbs": hbm_peak,
+        "hbm_peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
+        "algorithmic_bytes_per_launch": algo_bytes, "traffic": traffic, "traffic_source": traffic_source,
+        "kernel": dec.kernel_name, "kernel_ms": dec_ms,
+        "kernel_share_of_step": dec_ms / ms_step,
+    }
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on one host core, bounded sample
     cpu = None
@@ -325,26 +509,39 @@ def run_gpu(args) -> int:
                                                   f"unmodified ({dt2:.1f} s); GPU output bit-exact on all of them"}
             d249.close()
 
+    # ---- the other BASELINE configs, same run (N=1 only: they are per-GPU kernels)
+    del metrics, payload
+    torch.cuda.empty_cache()
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = run_configs(cc, torch, local, alu_peak_ops, hbm_peak, args.quick)
+
     line = {
         "metric": METRIC, "value": gbit, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(F, world),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "kernel": dec.kernel_name,
-                     "kernel_ms": kern_ms, "note": "ACS is ALU-bound (min-plus recurrence); see alu_roofline"},
-        "alu_roofline": alu,
+        "step": "decode the rank's frames + count bit/frame errors + NCCL all-reduce of the 3 counters, all inside the timed region",
+        "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_gbit, "unit": UNIT, "h2d_bytes_per_step": Fe * dec.in_bytes, "d2h_bytes_per_step": Fe * dec.out_bytes,
-                "frames_per_step": Fe, "api": "vdec_decode_host (pinned host buffers, 2-stream pipeline)"},
+                "frames_per_step": Fe, "api": "vdec_decode_host (pinned host buffers, 2-stream pipeline)",
+                "h2d_gbs": e2e_h2d_gbs, "h2d_peak_gbs": h2d_peak_gbs, "frac_of_h2d_peak": e2e_h2d_gbs / h2d_peak_gbs,
+                "h2d_peak_how": f"{world} rank(s) at once, 8 x cudaMemcpyAsync of 256 MiB from pinned host memory, nothing else running",
+                "cpu_affinity": affinity},
         "e2e_iq": {"value": e2e_iq_gbit, "unit": UNIT, "h2d_bytes_per_step": Fe * code.T * 8, "d2h_bytes_per_step": Fe * dec.out_bytes,
-                   "frames_per_step": Fe, "api": "vdec_decode_iq_host (raw I/Q in, demapper on the GPU; SURVEY 8f-2)"},
+                   "frames_per_step": Fe, "h2d_gbs": e2e_iq_h2d_gbs, "frac_of_h2d_peak": e2e_iq_h2d_gbs / h2d_peak_gbs, "kernel": iq_kernel,
+                   "api": "vdec_decode_iq_host (raw I/Q in, demapper inside the decoder kernel; SURVEY 8f-2)"},
         "e2e_hard": {"value": e2e_hard_gbit, "unit": UNIT, "h2d_bytes_per_step": Fh * code.T, "d2h_bytes_per_step": Fh * (dec.out_bytes + 4),
-                     "frames_per_step": Fh, "kernel": hard_kernel,
+                     "frames_per_step": Fh, "kernel": hard_kernel, "h2d_gbs": e2e_hard_h2d_gbs, "frac_of_h2d_peak": e2e_hard_h2d_gbs / h2d_peak_gbs,
                      "api": "vdec_decode_host, VDEC_HARD_U16 (the BSC decoder's input: one symbol byte per step), same code and frame length"},
+        "link": {"value": link_gbit, "unit": UNIT, "frames_per_step": Fl, "ms_per_step": float(tl.item()), "kernel": iq_kernel,
+                 "what": "GPU-resident link step of config 5 (SURVEY 8f-1): synthetic source -> encoder -> mapper -> AWGN (raw I/Q to HBM) -> "
+                         "demapper + decoder in one kernel -> error count; nothing touches the host"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "acs_gstate_updates_per_s": world * state_updates / 1e9,
-        "bit_errors": {"bits": counters[0], "bit_errors": counters[1], "frame_errors": counters[2]},
+        "acs_gstate_updates_per_s": world * F * code.T * code.S / (ms_step * 1e-3) / 1e9,
+        "bit_errors": {"bits": totals[0], "bit_errors": totals[1], "frame_errors": totals[2], "ranks_summed": world},
+        "configs": configs,
     }
     _emit(line)
     if world > 1:
@@ -371,6 +568,8 @@ def main() -> int:
     ap.add_argument("--e2e-frames", type=int, default=65536)
     ap.add_argument("--cpu-frames", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config table (N=1 only)")
+    ap.add_argument("--quick", type=int, default=1, help="divide the frame counts of the per-config table by this")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

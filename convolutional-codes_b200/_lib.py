@@ -15,6 +15,12 @@ class VdecConfig(C.Structure):
                 ("metric_max", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class VdecSweepConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("frames_per_batch", C.c_uint64), ("max_frames", C.c_uint64),
+                ("min_frame_errors", C.c_uint64), ("chunk_frames", C.c_uint32), ("channel", C.c_uint32),
+                ("resume_path", C.c_char_p)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "vdec_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VdecConfig)]),
@@ -23,6 +29,7 @@ EXPORTS = {
     "vdec_config_labels": (C.c_int, [C.POINTER(VdecConfig), C.c_void_p]),
     "vdec_config_kernel_name": (C.c_char_p, [C.POINTER(VdecConfig)]),
     "vdec_jit_check": (C.c_long, [C.POINTER(VdecConfig)]),
+    "vdec_jit_check_iq": (C.c_long, [C.POINTER(VdecConfig)]),
     "vdec_steps": (C.c_uint32, [C.c_void_p]),
     "vdec_states": (C.c_uint32, [C.c_void_p]),
     "vdec_in_bytes_per_frame": (C.c_size_t, [C.c_void_p]),
@@ -41,6 +48,11 @@ EXPORTS = {
     "vdec_demap_device": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "vdec_synth_awgn_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_float, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vdec_hard_demap_device": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "vdec_iq_kernel_name": (C.c_char_p, [C.c_void_p]),
+    "vdec_sweep": (C.c_int, [C.POINTER(VdecConfig), C.c_void_p, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_int), C.c_int,
+                             C.POINTER(C.c_uint64)]),
+    "vdec_device_count": (C.c_int, []),
     "vdec_synth_bsc_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
 }

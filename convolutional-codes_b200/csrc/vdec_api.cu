@@ -43,6 +43,8 @@ struct vdec_priv {
     float* iq_dev[2];         // device staging of host I/Q, per pipeline stage
     uint8_t* iq_out[2];       // and of the decoded output
     size_t iq_frames;
+    const vd::JitEntry* jit_iq;   // run-time compiled register kernel with the raw-I/Q feeder (compiled on first use)
+    bool jit_iq_tried;
 };
 
 static vdec_priv* priv(vdec_t* h) { return reinterpret_cast<vdec_priv*>(h); }
@@ -60,13 +62,36 @@ static int ensure_scratch(vdec_priv* p, int slot, const vd::LaunchGeom& geom, ui
     return 0;
 }
 
-// raw I/Q -> metrics (demap kernel) -> decode, in chunks that bound the metric staging buffer
 static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframes, uint8_t* out_dev, int32_t* pm_dev,
                      cudaStream_t st);
+static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const void* in_dev, uint64_t nframes,
+                       uint8_t* out_dev, int32_t* pm_dev, cudaStream_t st, bool iq = false);
+
+// does this handle decode raw I/Q inside its decoder kernel (metrics formed in the feeder, vdec_regs.cuh IqRing)?
+static bool iq_fused(vdec_priv* p) {
+    vdec* h = &p->base;
+    if (h->cfg.metric != VDEC_SOFT_F32) return false;
+    if (h->regs) return h->regs->launch_iq != nullptr;
+    if (h->jit && vd::jit_family(h->jit) == vd::kJitRegs) {
+        if (!p->jit_iq_tried) {
+            p->jit_iq_tried = true;
+            char why[2048] = "";
+            p->jit_iq = vd::jit_get(&h->cfg, vd::kJitRegsIq, VDEC_SOFT_F32, why, sizeof(why));
+            if (!p->jit_iq && why[0] && getenv("VDEC_QUIET") == nullptr)
+                fprintf(stderr, "[vdec] raw-I/Q kernel not compiled, using the separate demapper: %s\n", why);
+        }
+        return p->jit_iq != nullptr;
+    }
+    return false;
+}
+
+// Raw I/Q in.  Register kernels (K <= 7) form the branch metrics in their feeder: one launch, 8 B of HBM per step.
+// The other families go through the stand-alone demapper into a bounded staging buffer.
 static int decode_iq_on(vdec_priv* p, int slot, const float* iq_dev, uint64_t nframes, uint8_t* out_dev, cudaStream_t st) {
     vdec* h = &p->base;
     if (h->cfg.metric != VDEC_SOFT_F32) { vd::set_error("raw-I/Q entry needs the soft metric"); return -1; }
     const vd::LaunchGeom& g = h->geom;
+    if (iq_fused(p)) return decode_geom(p, slot, g, iq_dev, nframes, out_dev, nullptr, st, true);
     size_t chunk = ((size_t)1 << 30) / ((size_t)g.T * g.M * 4);      // ~1 GiB of staged metrics
     if (chunk < 1) chunk = 1;
     if (chunk > nframes) chunk = nframes;
@@ -86,9 +111,9 @@ static int decode_iq_on(vdec_priv* p, int slot, const float* iq_dev, uint64_t nf
 
 // decode `nframes` frames of geometry `geom` (geom.T steps each, starts geom.stride_steps apart)
 static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const void* in_dev, uint64_t nframes,
-                       uint8_t* out_dev, int32_t* pm_dev, cudaStream_t st) {
+                       uint8_t* out_dev, int32_t* pm_dev, cudaStream_t st, bool iq) {
     vdec* h = &p->base;
-    const size_t step_bytes = vd::in_bytes_per_frame(h) / h->geom.T;
+    const size_t step_bytes = iq ? 2 * sizeof(float) : vd::in_bytes_per_frame(h) / h->geom.T;
     uint64_t done = 0;
     while (done < nframes) {
         const uint32_t n = (uint32_t)((nframes - done < h->max_frames) ? (nframes - done) : h->max_frames);
@@ -101,7 +126,8 @@ static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const
         uint8_t* out = out_dev + done * g.out_bytes;
         int32_t* pm = pm_dev ? pm_dev + done : nullptr;
         int rc;
-        if (h->jit) rc = vd::jit_run(h->jit, g, in, out, pm, p->sc.p[slot], st);
+        if (iq) rc = h->regs ? h->regs->launch_iq(g, in, out, pm, p->sc.p[slot], st) : vd::jit_run(p->jit_iq, g, in, out, pm, p->sc.p[slot], st);
+        else if (h->jit) rc = vd::jit_run(h->jit, g, in, out, pm, p->sc.p[slot], st);
         else if (h->tile2) rc = vd::tile2_run(h->tile2, g, in, out, pm, p->sc.p[slot], st);
         else if (h->tile) rc = vd::tile_run(h->tile, g, in, out, p->sc.p[slot], st);
         else if (h->regsw) rc = vd::regsw_run(h->regsw, g, in, out, p->sc.p[slot], st);
@@ -120,6 +146,44 @@ static int decode_on(vdec_priv* p, int slot, const void* in_dev, uint64_t nframe
                      cudaStream_t st) {
     return decode_geom(p, slot, p->base.geom, in_dev, nframes, out_dev, pm_dev, st);
 }
+
+
+// 16-byte alignment of float inputs: the soft kernels stage rows with 16-byte cp.async / vector loads, and a misaligned
+// device pointer would fault the context instead of returning -1
+static bool aligned_input(const vdec* h, const void* in_dev, const char* who) {
+    if (h->cfg.metric == VDEC_SOFT_F32 && (reinterpret_cast<uintptr_t>(in_dev) & 15u) != 0) {
+        vd::set_error("%s: soft input must be 16-byte aligned", who);
+        return false;
+    }
+    return true;
+}
+
+// packed 16-bit families: limits that depend on the number of steps of a launch
+static bool packed_limits_ok(const vdec_config& cfg, uint64_t T) {
+    const uint64_t mx = cfg.metric == VDEC_HARD_U16 ? cfg.symlen_out : (cfg.metric_max ? cfg.metric_max : 255);
+    if (T * mx >= 0x4000u) return false;
+    return cfg.constr_len >= 8 || T * 32 <= 200 * 1024;          // register kernels: output tile in shared memory
+}
+
+// vdec_stream_decode_device: swap the handle's kernel family for the duration of one call when the window geometry
+// breaks the limits of the selected one (restored on scope exit; a handle has one call in flight at a time)
+struct StreamSelGuard {
+    vdec* h;
+    const vd::RegsEntry* regs; const vd::Regs2Entry* regs2; const vd::Tile2Entry* tile2; const vd::JitEntry* jit;
+    bool swapped;
+    StreamSelGuard(vdec* h_, uint32_t window_T) : h(h_), regs(h_->regs), regs2(h_->regs2), tile2(h_->tile2), jit(h_->jit), swapped(false) {
+        const bool packed = h->regs2 || h->tile2 ||
+                            (h->jit && (vd::jit_family(h->jit) == vd::kJitRegs2 || vd::jit_family(h->jit) == vd::kJitTile2));
+        const bool regs_too_long = (h->regs || (h->jit && vd::jit_family(h->jit) == vd::kJitRegs)) && (uint64_t)window_T * 16 > 200 * 1024;
+        if ((packed && !packed_limits_ok(h->cfg, window_T)) || regs_too_long) {
+            swapped = true;
+            h->regs2 = nullptr; h->tile2 = nullptr; h->jit = nullptr; h->regs = nullptr;
+            if (!regs_too_long && h->cfg.metric == VDEC_HARD_U16 && h->cfg.constr_len <= 7 && (uint64_t)window_T * 16 <= 200 * 1024)
+                h->regs = vd::regs_find(h->cfg.constr_len, h->cfg.symlen_out, VDEC_HARD_U16, h->labels_host);
+        }
+    }
+    ~StreamSelGuard() { if (swapped) { h->regs = regs; h->regs2 = regs2; h->tile2 = tile2; h->jit = jit; } }
+};
 
 static const char* metric_tag(uint32_t metric) {
     return metric == VDEC_HARD_U16 ? "hard_u16" : metric == VDEC_SOFT_U8 ? "soft_u8" : "soft_f32";
@@ -176,6 +240,16 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
     if (cfg->constr_len < 2 || cfg->constr_len > 15) { vd::set_error("constr_len %u unsupported (2..15)", cfg->constr_len); return -1; }
     if (cfg->block_len < 1 || cfg->block_len > (1u << 24)) { vd::set_error("block_len %u unsupported", cfg->block_len); return -1; }
     if (cfg->metric > VDEC_SOFT_U8 || cfg->parity > VDEC_PARITY_LINEAR) { vd::set_error("bad metric/parity selector"); return -1; }
+    if (cfg->metric == VDEC_SOFT_U8) {
+        // the integer kernels sum exactly; the reference sums the same integers in fp32, which is exact (hence equal) only
+        // while every path metric stays below 2^24
+        const uint64_t Tq = (uint64_t)cfg->block_len + cfg->constr_len - 1, mx = cfg->metric_max ? cfg->metric_max : 255;
+        if (Tq * mx >= (1ull << 24)) {
+            vd::set_error("VDEC_SOFT_U8: (block_len + constr_len - 1) * metric_max = %llu reaches 2^24, where the reference's fp32 sums "
+                          "stop being exact; use VDEC_SOFT_F32", (unsigned long long)(Tq * mx));
+            return -1;
+        }
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         vd::set_error("no CUDA device: this library has no CPU path"); return -1;
@@ -329,6 +403,17 @@ long vdec_jit_check(const struct vdec_config* cfg) {
     return n;
 }
 
+long vdec_jit_check_iq(const struct vdec_config* cfg) {
+    static thread_local uint8_t labels[2 * 16384];
+    if (vdec_config_labels(cfg, labels) != 0) return -1;
+    int family = 0; uint32_t mode = 0;
+    if (cfg->metric != VDEC_SOFT_F32 || !vd::jit_pick(cfg, labels, &family, &mode, nullptr, 0) || family != vd::kJitRegs) return 0;
+    char why[2048] = "";
+    const long n = vd::jit_compile_check(cfg, vd::kJitRegsIq, VDEC_SOFT_F32, why, sizeof(why));
+    if (n < 0) vd::set_error("run-time compilation failed: %s", why);
+    return n;
+}
+
 int vdec_labels(const vdec_t* h, uint8_t* labels) {
     if (!h || !labels) { vd::set_error("vdec_labels: null argument"); return -1; }
     memcpy(labels, h->labels_host, 2 * h->geom.S);
@@ -339,6 +424,7 @@ int vdec_decode_device(vdec_t* h, const void* in_dev, uint64_t nframes, uint8_t*
                        void* cuda_stream) {
     if (!h || (nframes && (!in_dev || !out_dev))) { vd::set_error("vdec_decode_device: null argument"); return -1; }
     if (nframes == 0) return 0;
+    if (!aligned_input(h, in_dev, "vdec_decode_device")) return -1;
     VDEC_CUDA(cudaSetDevice(h->device));
     return decode_on(priv(h), 0, in_dev, nframes, out_dev, path_metric_dev, static_cast<cudaStream_t>(cuda_stream));
 }
@@ -394,6 +480,7 @@ int vdec_decode_host(vdec_t* h, const void* in_host, uint64_t nframes, uint8_t* 
 int vdec_decode_iq_device(vdec_t* h, const float* iq_dev, uint64_t nframes, uint8_t* out_dev, void* cuda_stream) {
     if (!h || (nframes && (!iq_dev || !out_dev))) { vd::set_error("vdec_decode_iq_device: null argument"); return -1; }
     if (nframes == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(iq_dev) & 15u) != 0) { vd::set_error("vdec_decode_iq_device: iq_dev must be 16-byte aligned"); return -1; }
     VDEC_CUDA(cudaSetDevice(h->device));
     return decode_iq_on(priv(h), 0, iq_dev, nframes, out_dev, static_cast<cudaStream_t>(cuda_stream));
 }
@@ -466,7 +553,12 @@ int vdec_stream_decode_device(vdec_t* h, const void* in_dev, uint64_t nsteps, ui
     if (depth > block_steps) { vd::set_error("depth must not exceed block_steps"); return -1; }
     if ((uint64_t)block_steps + 2ull * depth > 8192) { vd::set_error("block_steps + 2*depth must not exceed 8192"); return -1; }
     if (nsteps == 0) return 0;
+    if (!aligned_input(h, in_dev, "vdec_stream_decode_device")) return -1;
     vdec_priv* p = priv(h);
+    // The kernel family was chosen for frames of block_len steps; the windows are block_steps + 2*depth long.  The packed
+    // 16-bit families have no renormalisation (T * metric_max < 2^14) and stage 32 B per step in shared memory: when
+    // the window breaks either limit this call runs on the 32-bit register kernel or the table-driven kernels instead.
+    StreamSelGuard guard(h, (uint32_t)((uint64_t)block_steps + 2ull * depth < nsteps ? block_steps + 2 * depth : nsteps));
     VDEC_CUDA(cudaSetDevice(h->device));
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const uint8_t* in = static_cast<const uint8_t*>(in_dev);
@@ -509,9 +601,23 @@ int vdec_demap_device(uint32_t symlen_out, const float* iq_dev, uint64_t nsym, f
     return vd::demap_launch(symlen_out, iq_dev, nsym, metrics_dev, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int vdec_hard_demap_device(uint32_t symlen_out, const float* iq_dev, uint64_t nsym, float* metrics_dev, void* cuda_stream) {
+    if (!iq_dev || !metrics_dev) { vd::set_error("vdec_hard_demap_device: null argument"); return -1; }
+    return vd::demap_launch(symlen_out, iq_dev, nsym, metrics_dev, static_cast<cudaStream_t>(cuda_stream), true);
+}
+
+const char* vdec_iq_kernel_name(vdec_t* h) {
+    if (!h || h->cfg.metric != VDEC_SOFT_F32) return "";
+    vdec_priv* p = priv(h);
+    static thread_local char name[192];
+    if (iq_fused(p)) snprintf(name, sizeof(name), "%s + demapper in the feeder (raw I/Q ring)", h->regs ? h->regs->name : vd::jit_name(p->jit_iq));
+    else snprintf(name, sizeof(name), "demap_kernel -> %s", h->kernel_name);
+    return name;
+}
+
 int vdec_synth_awgn_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uint64_t seed, float sigma,
                            uint8_t* payload_dev, float* metrics_dev, float* iq_dev, void* cuda_stream) {
-    if (!h || !payload_dev || !metrics_dev) { vd::set_error("vdec_synth_awgn_device: null argument"); return -1; }
+    if (!h || !payload_dev || (!metrics_dev && !iq_dev)) { vd::set_error("vdec_synth_awgn_device: null argument"); return -1; }
     VDEC_CUDA(cudaSetDevice(h->device));
     h->launches += 2;
     return vd::synth_awgn_launch(h->geom, h->labels_dev, nframes, first_frame, seed, sigma, payload_dev, metrics_dev, iq_dev,

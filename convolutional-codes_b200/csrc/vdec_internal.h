@@ -52,6 +52,9 @@ struct RegsEntry {
     uint8_t labels[128];                       // [S][2]
     int (*launch)(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric,
                   uint32_t* surv, cudaStream_t st);
+    // soft entries only: the same kernel fed with raw I/Q [frame][step][2], branch metrics formed in the feeder
+    int (*launch_iq)(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric,
+                     uint32_t* surv, cudaStream_t st);
     size_t (*surv_bytes)(const LaunchGeom& g);
 };
 const RegsEntry* regs_find(uint32_t K, uint32_t n, uint32_t metric, const uint8_t* labels);
@@ -90,11 +93,12 @@ size_t tile2_bytes(const Tile2Entry* e, const LaunchGeom& g);
 
 // ---- run-time compiled instantiations of the four families above (vdec_jit.cu, NVRTC) -----------------------
 struct JitEntry;
-enum { kJitRegs = 0, kJitRegs2 = 1, kJitTile = 2, kJitTile2 = 3 };
+enum { kJitRegs = 0, kJitRegs2 = 1, kJitTile = 2, kJitTile2 = 3, kJitRegsIq = 4 /* kJitRegs soft with the raw-I/Q feeder */ };
 bool jit_enabled(const vdec_config* cfg);
 bool jit_pick(const vdec_config* cfg, const uint8_t* labels, int* family, uint32_t* mode, char* name, size_t name_len);
 const JitEntry* jit_get(const vdec_config* cfg, int family, uint32_t mode, char* err, size_t errlen);
 const char* jit_name(const JitEntry* e);
+int jit_family(const JitEntry* e);
 int jit_launches(const JitEntry* e);
 size_t jit_bytes(const JitEntry* e, const LaunchGeom& g);
 int jit_run(const JitEntry* e, const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* scratch,
@@ -113,7 +117,7 @@ int count_errors_launch(const uint8_t* dec, const uint8_t* payload, uint64_t nfr
                         uint32_t out_bytes, uint64_t* counters, cudaStream_t st);
 int stitch_launch(const uint8_t* tmp, uint32_t row_bytes, uint32_t skip_bytes, uint64_t nblk, uint64_t keep_bytes,
                   uint64_t last_keep_bytes, uint8_t* out, cudaStream_t st);
-int demap_launch(uint32_t n, const float* iq, uint64_t nsym, float* metrics, cudaStream_t st);
+int demap_launch(uint32_t n, const float* iq, uint64_t nsym, float* metrics, cudaStream_t st, bool hard = false);
 int synth_awgn_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t nframes, uint64_t first_frame,
                       uint64_t seed, float sigma, uint8_t* payload, float* metrics, float* iq, cudaStream_t st);
 int synth_bsc_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t nframes, uint64_t first_frame,

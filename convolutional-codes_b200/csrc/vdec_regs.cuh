@@ -30,10 +30,17 @@
 #include <utility>
 
 #include "vdec_internal.h"
+#include "vdec_demap.cuh"
 
 // tuning knobs for A/B builds (tools/build_variant.py)
 #ifndef VDEC_MINB_REF
 #define VDEC_MINB_REF 4
+#endif
+#ifndef VDEC_MINB_LIN
+#define VDEC_MINB_LIN 3
+#endif
+#ifndef VDEC_SIGN_LIN
+#define VDEC_SIGN_LIN 0
 #endif
 
 namespace vd {
@@ -45,8 +52,8 @@ struct CodeDef {
     // resident CTAs per SM the register budget is cut for.  Measured (tools/bench_configs.py, A/B of
     // builds): labellings with fewer shared candidate sums, and n = 3, spill at 128 registers and run
     // 5 % faster with 168 registers and 3 CTAs; the reference-labelled (171,133) code prefers 4.
-    static constexpr int kMinBlocks = (K_ == 7 && !(N_ == 2 && REF_)) ? 3 : VDEC_MINB_REF;
-    static constexpr bool kSignDecisions = (N_ == 2 && REF_);      // survivor bits from packed differences, see kDecSign
+    static constexpr int kMinBlocks = (K_ == 7 && !(N_ == 2 && REF_)) ? VDEC_MINB_LIN : VDEC_MINB_REF;
+    static constexpr bool kSignDecisions = (N_ == 2 && (REF_ || VDEC_SIGN_LIN));      // survivor bits from packed differences, see kDecSign
     VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {
         const uint64_t p[3] = {P0_, P1_, P2_};
         return branch_label(K_, N_, p, REF_, s, i);
@@ -58,15 +65,7 @@ struct CodeDef {
 #endif
 constexpr int kRegsThreads = VDEC_REGS_THREADS;
 
-// compile-time loop: f(integral_constant<int, I>) for I in [I0, N)
-template <int I0, class F, int... Is>
-__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, Is...>) {
-    (f(std::integral_constant<int, I0 + Is>{}), ...);
-}
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (I < N) static_for_impl<I>(f, std::make_integer_sequence<int, N - I>{});
-}
+// static_for<I, N>(f): compile-time loop, defined in vdec_demap.cuh
 
 // ---- metric policies -----------------------------------------------------------------------
 struct SoftF32 {
@@ -124,6 +123,16 @@ struct HardU16 {
     }
     template <int M> VDEC_HD static constexpr size_t step_elems() { return 1; }
 };
+
+// Soft decisions from RAW I/Q: the input is what the channel hands to the demapper
+// (AWGN-channel/main.c:104), float32 [frame][step][2]; the M branch metrics of a step are formed in the feeder
+// (IqRing) with the demapper's own arithmetic (vdec_demap.cuh), so the decoder reads 8 B per step instead of 4 M.
+struct SoftIq : SoftF32 {
+    static constexpr bool kIq = true;
+    template <int M> VDEC_HD static constexpr size_t step_elems() { return 2; }
+};
+template <class MP> constexpr bool kIsIq = false;
+template <> constexpr bool kIsIq<SoftIq> = true;
 
 // ---- one trellis step at rotation phase PH ---------------------------------------------------
 template <class CD, class MP, int PH>
@@ -474,6 +483,69 @@ struct SoftRing {
     __device__ __forceinline__ void drain() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 };
 
+// Raw I/Q rows: 8 B per step.  Same private ring as SoftRing with 8-byte pieces (cp.async.ca), one LDGSTS per step
+// as before; the consumer reads its step with one conflict-free LDS.64 and computes the M metrics in registers:
+// per point 2 subtractions + 2 squares per distinct coordinate, one add and the 3-operation exact division per
+// metric (vdec_demap.cuh) — 24 FMA-pipe operations per step for n = 2, against ~200 issue slots of ACS.
+template <int N, int B>
+struct IqRing {
+    static constexpr int M = 1 << N;
+    static constexpr int G = B, NG = 3, kSlots = G * NG;
+    static constexpr uint32_t kPieceStride = 32 * 8;
+    static constexpr uint32_t kGroupBytes = (uint32_t)G * kPieceStride;
+    static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * 8;            // K = 7: 4.5 KB
+
+    uint32_t base, T;
+    const float* nextp;
+    uint32_t next_t, woff, roff;
+
+    template <int OFF_S, int OFF_G>
+    static __device__ __forceinline__ void copy_piece(uint32_t dst, const float* src) {
+        asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 8;" ::"r"(dst), "l"(src), "n"(OFF_S), "n"(OFF_G) : "memory");
+    }
+    __device__ __forceinline__ void prefetch_next() {
+        const uint32_t dst = base + woff;
+        if (next_t + G <= T) {
+            static_for<0, G>([&](auto ic) {
+                constexpr int I = decltype(ic)::value;
+                copy_piece<I * (int)kPieceStride, I * 8>(dst, nextp);
+            });
+        } else {
+            static_for<0, G>([&](auto ic) {
+                constexpr int I = decltype(ic)::value;
+                if (next_t + I < T) copy_piece<I * (int)kPieceStride, I * 8>(dst, nextp);
+            });
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        nextp += G * 2; next_t += G;
+        woff = (woff == (NG - 1) * kGroupBytes) ? 0u : woff + kGroupBytes;
+    }
+    __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
+        base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * 8;
+        T = steps; nextp = row; next_t = 0; woff = 0; roff = 0;
+        prefetch_next();
+        prefetch_next();
+    }
+    __device__ __forceinline__ void begin_period() {
+        prefetch_next();
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+    }
+    __device__ __forceinline__ void end_period() { roff = (roff == (NG - 1) * kGroupBytes) ? 0u : roff + kGroupBytes; }
+    template <uint64_t MASK, int PH>
+    __device__ __forceinline__ void get_pairs(uint64_t (&bp)[M * M]) const {
+        float x, y;
+        asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(x), "=f"(y) : "r"(base + roff), "n"(PH * (int)kPieceStride));
+        float bm[M];
+        demap_point<N>(x, y, bm);
+        static_for<0, M * M>([&](auto ic) {
+            constexpr int I = decltype(ic)::value, a = I / M, b = I % M;
+            if constexpr ((MASK >> I) & 1ull) asm("mov.b64 %0, {%1, %2};" : "=l"(bp[I]) : "f"(bm[a]), "f"(bm[b]));
+            else bp[I] = 0;
+        });
+    }
+    __device__ __forceinline__ void drain() const { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+};
+
 // Hard symbols are one byte per step; a warp's 32 frames are contiguous (32*T bytes), so plain
 // read-only loads stay in L1.
 template <int M, int B>
@@ -500,6 +572,7 @@ template <class MP, int M, int B> struct FeederOf;
 #endif
 template <int M, int B> struct FeederOf<SoftF32, M, B> { using type = SoftRing<M, B, (M == 8 ? VDEC_RING_PB_M8 : VDEC_RING_PB_M4)>; };
 template <int M, int B> struct FeederOf<HardU16, M, B> { using type = HardDirect<M, B>; };
+template <int M, int B> struct FeederOf<SoftIq, M, B> { using type = IqRing<(M == 2 ? 1 : M == 4 ? 2 : 3), B>; };
 
 #ifndef VDEC_TRACE_CHUNK
 #define VDEC_TRACE_CHUNK 16
@@ -739,9 +812,9 @@ struct RegsShape {
     uint32_t nw;            // survivor words per step and frame
     size_t ring_bytes;      // input ring per warp
 };
-inline RegsShape regs_shape(uint32_t K, uint32_t n, uint32_t metric) {
+inline RegsShape regs_shape(uint32_t K, uint32_t n, uint32_t metric, bool iq = false) {
     const uint32_t S = 1u << (K - 1), M = 1u << n;
-    return RegsShape{(S + 31) / 32, metric == VDEC_SOFT_F32 ? (size_t)(K - 1) * 3 * 32 * M * 4 : 0};
+    return RegsShape{(S + 31) / 32, metric == VDEC_SOFT_F32 ? (size_t)(K - 1) * 3 * 32 * (iq ? 8 : M * 4) : 0};
 }
 
 // `kern` is a __global__ symbol of this library or a cudaKernel_t of a run-time compiled module
@@ -768,7 +841,7 @@ template <class CD, class MP>
 int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
     using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
     constexpr RegsShape sh{(uint32_t)CD::NW, Feeder::kWarpBytes};
-    static_assert(Feeder::kWarpBytes == (MP::kMetric == VDEC_SOFT_F32 ? (size_t)CD::B * 3 * 32 * CD::M * 4 : 0),
+    static_assert(Feeder::kWarpBytes == (MP::kMetric == VDEC_SOFT_F32 ? (size_t)CD::B * 3 * 32 * (kIsIq<MP> ? 8 : CD::M * 4) : 0),
                   "regs_shape() must describe the feeder");
     return regs_launch_kernel(reinterpret_cast<const void*>(&vit_regs_kernel<CD, MP>), sh, g, in, out, path_metric, surv, st);
 }
@@ -782,6 +855,7 @@ RegsEntry make_regs_entry(const char* name) {
     e.name = name; e.K = CD::K; e.n = CD::N; e.metric = MP::kMetric;
     for (int s = 0; s < CD::S; ++s) { e.labels[2 * s] = (uint8_t)CD::label(s, 0); e.labels[2 * s + 1] = (uint8_t)CD::label(s, 1); }
     e.launch = &regs_launch<CD, MP>;
+    if constexpr (std::is_same_v<MP, SoftF32>) e.launch_iq = &regs_launch<CD, SoftIq>;      // raw-I/Q entry, metrics formed in the feeder
     e.surv_bytes = &regs_surv_bytes<CD>;
     return e;
 }

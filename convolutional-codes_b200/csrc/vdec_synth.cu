@@ -8,13 +8,13 @@
 // reference draws from libc rand() with a time seed (main.c:147), so there is no bit-level parity
 // target for the noise itself; the deterministic parts (encoder labels, mapper points, demapper
 // arithmetic) are bit-exact and tested against the oracle.
-#include "vdec_internal.h"
+#include "vdec_demap.cuh"
 
 namespace vd {
 
 namespace {
 
-// constellation points: DATA of common/constellations.c:8-25 (unit power, Gray mapped)
+// constellation points, interleaved (x, y): the table of vdec_demap.cuh's cst_x / cst_y (common/constellations.c:8-25)
 __constant__ float c_cst1[4] = {0.707107f, 0.707107f, -0.707107f, -0.707107f};
 __constant__ float c_cst2[8] = {0.707107f, 0.707107f, 0.707107f, -0.707107f, -0.707107f, 0.707107f, -0.707107f, -0.707107f};
 __constant__ float c_cst3[16] = {0.408248f, 0.408248f, 0.408248f, 1.224745f, -0.408248f, 0.408248f, -1.224745f, 0.408248f,
@@ -35,11 +35,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-// demapper.c:66-70 with demapper.c:43-45 — explicit round-to-nearest ops, no FMA contraction
-__device__ __forceinline__ float ndist_of(const float* c) {
-    const float dx = __fsub_rn(c[0], c[2]), dy = __fsub_rn(c[1], c[3]);
-    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-}
+// demapper.c:66-70 with demapper.c:43-45 for a run-time n — explicit round-to-nearest ops, no FMA contraction,
+// IEEE division.  The stand-alone demap kernels use this form; the fused paths (synthetic source, decoder feeder) use
+// vdec_demap.cuh's three-operation exact division, and the tests compare the two bit for bit.
 __device__ __forceinline__ float demap_one(const float* c, uint32_t k, float x, float y, float nd) {
     const float dx = __fsub_rn(x, c[2 * k]), dy = __fsub_rn(y, c[2 * k + 1]);
     return __fdiv_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), nd);
@@ -64,50 +62,104 @@ __global__ void payload_kernel(uint64_t nframes, uint64_t first, uint64_t seed, 
     }
 }
 
-// encoder state before step t and input bit at step t, from the payload (encoder.c:84-119:
-// bits enter MSB-first; steps >= L are the zero tail)
-__device__ __forceinline__ uint32_t enc_symbol(const uint8_t* __restrict__ pl, uint32_t t, uint32_t K, uint32_t L,
+// Encoder output for step t of a frame (encoder.c:84-119: bits enter MSB-first, steps >= L are the zero tail):
+// label of (state before step t, input bit t), state bit K-2 = previous input (viterbi-decoder.c:65-66).
+// The K input bits t-K+1 .. t are cut out of three payload bytes; bits outside [0, L) read as zero.
+__device__ __forceinline__ uint32_t enc_symbol(const uint8_t* __restrict__ pl, uint32_t t, uint32_t K, uint32_t L, uint32_t pb,
                                                const uint8_t* __restrict__ labels) {
-    uint32_t state = 0;                                  // bit K-2 = previous input ... (viterbi-decoder.c:65-66)
-    for (uint32_t j = 1; j < K; ++j) {
-        uint32_t bit = 0;
-        if (t >= j && (t - j) < L) bit = (pl[(t - j) >> 3] >> (7 - ((t - j) & 7))) & 1u;
-        state |= bit << (K - 1 - j);
+    const int j = (int)(t >> 3);                                  // byte holding bit t
+    uint32_t w = 0;                                               // bits 8(j-2) .. 8j+7, bit 8(j-2) at position 23
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        const int jj = j - 2 + b;
+        const uint32_t v = (jj >= 0 && jj < (int)pb) ? (uint32_t)__ldg(pl + jj) : 0u;
+        w = (w << 8) | v;
     }
-    uint32_t in = 0;
-    if (t < L) in = (pl[t >> 3] >> (7 - (t & 7))) & 1u;
+    const int base = 8 * (j - 2);
+    const int keep = (int)L - base;                               // bits of w that belong to the payload
+    if (keep < 24) w = keep <= 0 ? 0u : (w & ~((1u << (24 - keep)) - 1u));
+    const uint32_t win = w >> (7u - (t & 7u));                    // bit t at position 0, bit t-i at position i
+    const uint32_t in = win & 1u;
+    const uint32_t state = __brev((win >> 1) & ((1u << (K - 1)) - 1u)) >> (33u - K);     // bit t-1 -> position K-2
     return labels[2 * state + in];
 }
 
-__global__ void synth_awgn_kernel(LaunchGeom g, const uint8_t* __restrict__ labels, uint64_t nframes, uint64_t first,
-                                  uint64_t seed, float sigma, const uint8_t* __restrict__ payload,
-                                  float* __restrict__ metrics, float* __restrict__ iq) {
-    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    if (i >= nframes * g.T) return;
-    const uint64_t f = i / g.T; const uint32_t t = (uint32_t)(i % g.T);
+// AWGN link for a run of symbols: payload -> encoder -> mapper -> noise [-> demapper].  One thread makes kPairs
+// PAIRS of consecutive symbols of the batch's [frame][step] sequence (one Philox call feeds one pair when both lie in
+// one frame at an even step, as all pairs do when T is even), so I/Q leaves as one 16-byte store per pair.
+constexpr int kSynthPairs = 4, kSynthThreads = 256;
+
+template <int N>
+__device__ __forceinline__ void synth_symbol(const LaunchGeom& g, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ payload,
+                                             const float* s_c, uint32_t f, uint32_t t, uint32_t w0, uint32_t w1, float sigma,
+                                             float& x, float& y) {
     const uint32_t pb = (g.L + 7) / 8;
-    const uint32_t sym = enc_symbol(payload + f * pb, t, g.K, g.L, labels);
-    const float* c = constellation(g.n);
-    uint32_t o[4];
-    const uint64_t F = first + f;
-    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)F, (uint32_t)(F >> 32), t, 0x4E4F4953u, o);
-    // Box-Muller: one pair per symbol (I, Q)   (gaussian.c:18-38 uses the same transform on rand())
-    const float u1 = ((float)(o[0] >> 8) + 1.0f) * (1.0f / 16777216.0f);     // (0, 1]
-    const float u2 = (float)(o[1] >> 8) * (1.0f / 16777216.0f);              // [0, 1)
-    const float rad = sqrtf(-2.0f * logf(u1));
+    const uint32_t sym = enc_symbol(payload + (size_t)f * pb, t, g.K, g.L, pb, labels);
+    // Box-Muller, one pair per symbol (I, Q)   (gaussian.c:18-38 uses the same transform on rand()); u1 in (0, 1]
+    // keeps the full 32 random bits where they matter (small u1 = large noise: tail to 6.7 sigma)
+    const float u1 = __fmaf_rn(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float ang = __fmaf_rn(__uint2float_rn(w1 >> 8), 3.7450702e-7f, -3.14159265f);      // [-pi, pi)
+    const float rad = sqrtf(fmaxf(-2.0f * __logf(u1), 0.0f));
     float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
-    const float x = __fadd_rn(c[2 * sym], __fmul_rn(sigma, rad * cs));       // main.c:100-102
-    const float y = __fadd_rn(c[2 * sym + 1], __fmul_rn(sigma, rad * sn));
-    if (iq != nullptr) { iq[2 * i] = x; iq[2 * i + 1] = y; }
-    const float nd = ndist_of(c);
-    float* dst = metrics + i * g.M;
-    if (g.M == 4) {
-        float4 v; v.x = demap_one(c, 0, x, y, nd); v.y = demap_one(c, 1, x, y, nd);
-        v.z = demap_one(c, 2, x, y, nd); v.w = demap_one(c, 3, x, y, nd);
-        *reinterpret_cast<float4*>(dst) = v;
-    } else {
-        for (uint32_t k = 0; k < g.M; ++k) dst[k] = demap_one(c, k, x, y, nd);
+    __sincosf(ang, &sn, &cs);
+    x = __fadd_rn(s_c[2 * sym], __fmul_rn(sigma, rad * cs));                                 // main.c:100-102
+    y = __fadd_rn(s_c[2 * sym + 1], __fmul_rn(sigma, rad * sn));
+}
+
+template <int N, bool MET, bool IQ>
+__global__ void __launch_bounds__(kSynthThreads)
+synth_awgn_kernel(LaunchGeom g, const uint8_t* __restrict__ labels, uint32_t nsym, uint64_t first, uint64_t seed, float sigma,
+                  const uint8_t* __restrict__ payload, float* __restrict__ metrics, float* __restrict__ iq) {
+    constexpr int M = 1 << N;
+    __shared__ float s_c[2 * M];
+    if (threadIdx.x < 2 * M) s_c[threadIdx.x] = constellation(N)[threadIdx.x];
+    __syncthreads();
+    const uint32_t T = g.T;
+    uint32_t s0 = 2u * (blockIdx.x * (uint32_t)(kSynthThreads * kSynthPairs) + threadIdx.x);       // first symbol of the pair
+    if (s0 >= nsym) return;
+    uint32_t f = s0 / T, t = s0 - f * T;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll 1
+    for (int r = 0; r < kSynthPairs; ++r) {
+        if (s0 >= nsym) break;
+        float x[2], y[2];
+        const bool two = s0 + 1 < nsym;
+        uint32_t o[4];
+        const uint64_t F = first + f;
+        philox4x32_10(k0, k1, (uint32_t)F, (uint32_t)(F >> 32), t >> 1, 0x4E4F4953u, o);
+        if (!(t & 1u) && t + 1 < T) {                             // the common case: one Philox call, both symbols
+            synth_symbol<N>(g, labels, payload, s_c, f, t, o[0], o[1], sigma, x[0], y[0]);
+            if (two) synth_symbol<N>(g, labels, payload, s_c, f, t + 1, o[2], o[3], sigma, x[1], y[1]);
+        } else {                                                  // odd T: the pair straddles two Philox blocks or two frames
+            synth_symbol<N>(g, labels, payload, s_c, f, t, o[2 * (t & 1u)], o[2 * (t & 1u) + 1], sigma, x[0], y[0]);
+            if (two) {
+                const uint32_t f1 = t + 1 < T ? f : f + 1, t1 = t + 1 < T ? t + 1 : 0;
+                const uint64_t F1 = first + f1;
+                philox4x32_10(k0, k1, (uint32_t)F1, (uint32_t)(F1 >> 32), t1 >> 1, 0x4E4F4953u, o);
+                synth_symbol<N>(g, labels, payload, s_c, f1, t1, o[2 * (t1 & 1u)], o[2 * (t1 & 1u) + 1], sigma, x[1], y[1]);
+            }
+        }
+        if constexpr (IQ) {
+            if (two) *reinterpret_cast<float4*>(iq + 2 * (size_t)s0) = make_float4(x[0], y[0], x[1], y[1]);
+            else *reinterpret_cast<float2*>(iq + 2 * (size_t)s0) = make_float2(x[0], y[0]);
+        }
+        if constexpr (MET) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (e == 1 && !two) break;
+                float bm[M];
+                demap_point<N>(x[e], y[e], bm);
+                float* dst = metrics + (size_t)(s0 + e) * M;
+                if constexpr (M == 2) *reinterpret_cast<float2*>(dst) = make_float2(bm[0], bm[1]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < M / 4; ++q)
+                        reinterpret_cast<float4*>(dst)[q] = make_float4(bm[4 * q], bm[4 * q + 1], bm[4 * q + 2], bm[4 * q + 3]);
+                }
+            }
+        }
+        s0 += 2u * kSynthThreads; t += 2u * kSynthThreads;
+        while (t >= T) { t -= T; ++f; }
     }
 }
 
@@ -117,7 +169,7 @@ __global__ void synth_bsc_kernel(LaunchGeom g, const uint8_t* __restrict__ label
     if (i >= nframes * g.T) return;
     const uint64_t f = i / g.T; const uint32_t t = (uint32_t)(i % g.T);
     const uint32_t pb = (g.L + 7) / 8;
-    uint32_t sym = enc_symbol(payload + f * pb, t, g.K, g.L, labels);
+    uint32_t sym = enc_symbol(payload + f * pb, t, g.K, g.L, pb, labels);
     uint32_t o[4];
     const uint64_t F = first + f;
     philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)F, (uint32_t)(F >> 32), t, 0x42534331u, o);
@@ -130,10 +182,31 @@ __global__ void demap_kernel(uint32_t n, const float* __restrict__ iq, uint64_t 
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= nsym) return;
     const float* c = constellation(n);
-    const float nd = ndist_of(c);
+    const float nd = ndist_rt((int)n);
     const float2 p = __ldg(reinterpret_cast<const float2*>(iq) + i);
     const uint32_t M = 1u << n;
     for (uint32_t k = 0; k < M; ++k) metrics[i * M + k] = demap_one(c, k, p.x, p.y, nd);
+}
+
+// common/hard-demapper.c:62-102: snap the received point to the nearest constellation point (squared distances
+// compared with strict '<', so the lowest index wins a tie, :68-77), then emit the soft demapper's expression
+// evaluated at the SNAPPED point (:81-87).
+__global__ void hard_demap_kernel(uint32_t n, const float* __restrict__ iq, uint64_t nsym, float* __restrict__ metrics) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= nsym) return;
+    const float* c = constellation(n);
+    const float nd = ndist_rt((int)n);
+    const float2 p = __ldg(reinterpret_cast<const float2*>(iq) + i);
+    const uint32_t M = 1u << n;
+    float best = __int_as_float(0x7f800000);
+    uint32_t idx = 0;
+    for (uint32_t k = 0; k < M; ++k) {
+        const float dx = __fsub_rn(p.x, c[2 * k]), dy = __fsub_rn(p.y, c[2 * k + 1]);
+        const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (d < best) { best = d; idx = k; }
+    }
+    const float sx = c[2 * idx], sy = c[2 * idx + 1];
+    for (uint32_t k = 0; k < M; ++k) metrics[i * M + k] = demap_one(c, k, sx, sy, nd);
 }
 
 // one thread per frame: compare the first L decoded bits with the payload (main.c:129-141)
@@ -197,23 +270,49 @@ int stitch_launch(const uint8_t* tmp, uint32_t row_bytes, uint32_t skip_bytes, u
     return 0;
 }
 
-int demap_launch(uint32_t n, const float* iq, uint64_t nsym, float* metrics, cudaStream_t st) {
+int demap_launch(uint32_t n, const float* iq, uint64_t nsym, float* metrics, cudaStream_t st, bool hard) {
     if (n < 1 || n > 3) { set_error("demap: symlen_out %u unsupported (constellations exist for 1..3)", n); return -1; }
     if (nsym == 0) return 0;
-    demap_kernel<<<grid_for(nsym, 256), 256, 0, st>>>(n, iq, nsym, metrics);
+    if (hard) hard_demap_kernel<<<grid_for(nsym, 256), 256, 0, st>>>(n, iq, nsym, metrics);
+    else demap_kernel<<<grid_for(nsym, 256), 256, 0, st>>>(n, iq, nsym, metrics);
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }
 
+template <int N>
+static int synth_awgn_n(const LaunchGeom& g, const uint8_t* labels_dev, uint32_t nsym, uint64_t first, uint64_t seed, float sigma,
+                        const uint8_t* payload, float* metrics, float* iq, cudaStream_t st) {
+    const unsigned grid = grid_for(((uint64_t)nsym + 1) / 2, kSynthThreads * kSynthPairs);
+    if (metrics && iq) synth_awgn_kernel<N, true, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
+    else if (metrics) synth_awgn_kernel<N, true, false><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
+    else synth_awgn_kernel<N, false, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
+    VDEC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// metrics and/or iq may be null (not both)
 int synth_awgn_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t nframes, uint64_t first, uint64_t seed,
                       float sigma, uint8_t* payload, float* metrics, float* iq, cudaStream_t st) {
     if (g.n < 1 || g.n > 3) { set_error("synth: symlen_out %u unsupported", g.n); return -1; }
+    if (!metrics && !iq) { set_error("synth: neither metrics nor I/Q requested"); return -1; }
     if (nframes == 0) return 0;
     const uint32_t pb = (g.L + 7) / 8;
     payload_kernel<<<grid_for(nframes * ((pb + 3) / 4), 256), 256, 0, st>>>(nframes, first, seed, pb, payload);
     VDEC_CUDA(cudaGetLastError());
-    synth_awgn_kernel<<<grid_for(nframes * g.T, 256), 256, 0, st>>>(g, labels_dev, nframes, first, seed, sigma, payload, metrics, iq);
-    VDEC_CUDA(cudaGetLastError());
+    // symbol indices are 32-bit inside a launch; launches start on even frame counts so that pairs stay aligned
+    uint64_t chunk = (0xF0000000ull / g.T) & ~1ull;    // head room: the kernel steps its 32-bit symbol index past the end
+    if (chunk < 2) chunk = 2;
+    for (uint64_t done = 0; done < nframes; done += chunk) {
+        const uint64_t nf = nframes - done < chunk ? nframes - done : chunk;
+        const uint32_t nsym = (uint32_t)(nf * g.T);
+        const uint8_t* pl = payload + done * pb;
+        float* met = metrics ? metrics + done * g.T * g.M : nullptr;
+        float* q = iq ? iq + done * g.T * 2 : nullptr;
+        int rc = g.n == 1 ? synth_awgn_n<1>(g, labels_dev, nsym, first + done, seed, sigma, pl, met, q, st)
+               : g.n == 2 ? synth_awgn_n<2>(g, labels_dev, nsym, first + done, seed, sigma, pl, met, q, st)
+                          : synth_awgn_n<3>(g, labels_dev, nsym, first + done, seed, sigma, pl, met, q, st);
+        if (rc != 0) return -1;
+    }
     return 0;
 }
 

@@ -50,11 +50,12 @@ def config_kernel_name(code: CodeParam, metric: int, parity: int = PARITY_REF, f
     return lib.vdec_config_kernel_name(C.byref(cfg)).decode()
 
 
-def jit_check(code: CodeParam, metric: int, parity: int = PARITY_REF, flags: int = 0, metric_max: int = 0) -> int:
-    """Compile (NVRTC, no GPU needed) the kernel an unregistered code would get; cubin bytes, 0 = nothing to compile."""
+def jit_check(code: CodeParam, metric: int, parity: int = PARITY_REF, flags: int = 0, metric_max: int = 0, iq: bool = False) -> int:
+    """Compile (NVRTC, no GPU needed) the kernel an unregistered code would get; cubin bytes, 0 = nothing to compile.
+    iq=True: the raw-I/Q variant of the register kernel (demapper in the feeder)."""
     lib = _lib.load()
     cfg = make_config(code, metric, parity, flags=flags, metric_max=metric_max)
-    n = lib.vdec_jit_check(C.byref(cfg))
+    n = (lib.vdec_jit_check_iq if iq else lib.vdec_jit_check)(C.byref(cfg))
     if n < 0:
         raise VdecError(_lib.last_error())
     return int(n)
@@ -194,19 +195,30 @@ class BatchDecoder:
             raise VdecError(_lib.last_error())
 
     # -- the stages either side of the decoder ----------------------------------------------------
-    def synth_awgn(self, nframes: int, first_frame: int, seed: int, sigma: float, want_iq: bool = False, stream=None):
+    def synth_awgn(self, nframes: int, first_frame: int, seed: int, sigma: float, want_iq: bool = False, stream=None,
+                   want_metrics: bool = True):
+        """GPU-resident source -> encoder -> mapper -> AWGN [-> soft demapper].  Returns (payload, metrics),
+        (payload, metrics, iq) with want_iq, or (payload, iq) with want_metrics=False (the cheap form, for decode_iq)."""
         import torch
+        assert want_metrics or want_iq
         dev = torch.device("cuda", self.device)
         c = self.code
         payload = torch.empty((nframes, c.payload_bytes), dtype=torch.uint8, device=dev)
-        metrics = torch.empty((nframes, c.T, c.M), dtype=torch.float32, device=dev)
+        metrics = torch.empty((nframes, c.T, c.M), dtype=torch.float32, device=dev) if want_metrics else None
         iq = torch.empty((nframes, c.T, 2), dtype=torch.float32, device=dev) if want_iq else None
         rc = self.lib.vdec_synth_awgn_device(self.h, nframes, first_frame, seed, sigma, C.c_void_p(payload.data_ptr()),
-                                             C.c_void_p(metrics.data_ptr()),
+                                             C.c_void_p(metrics.data_ptr()) if want_metrics else None,
                                              C.c_void_p(iq.data_ptr()) if want_iq else None, self._stream_ptr(stream))
         if rc != 0:
             raise VdecError(_lib.last_error())
+        if not want_metrics:
+            return payload, iq
         return (payload, metrics, iq) if want_iq else (payload, metrics)
+
+    @property
+    def iq_kernel_name(self) -> str:
+        """kernels behind decode_iq: fused (demapper in the decoder's feeder) or demap kernel + decoder"""
+        return (self.lib.vdec_iq_kernel_name(self.h) or b"").decode()
 
     def synth_bsc(self, nframes: int, first_frame: int, seed: int, crossover_ppm: int, stream=None):
         import torch
@@ -233,15 +245,41 @@ class BatchDecoder:
         return counters
 
 
-def demap(n: int, iq, stream=None):
-    """Soft demapper on the GPU, bit-exact to common/demapper.c:66-70.  iq: float32 [...,2] CUDA."""
+def demap(n: int, iq, stream=None, hard: bool = False):
+    """Demapper on the GPU: soft (bit-exact to common/demapper.c:66-70) or, with hard=True, the hard demapper
+    (common/hard-demapper.c:62-102: snap to the nearest point, then the same expression).  iq: float32 [...,2] CUDA."""
     import torch
     lib = _lib.load()
     assert iq.is_cuda and iq.is_contiguous() and iq.dtype == torch.float32
     nsym = iq.numel() // 2
     out = torch.empty(iq.shape[:-1] + (1 << n,), dtype=torch.float32, device=iq.device)
     s = stream if stream is not None else torch.cuda.current_stream(iq.device)
-    if lib.vdec_demap_device(n, C.c_void_p(iq.data_ptr()), nsym, C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream)) != 0:
+    fn = lib.vdec_hard_demap_device if hard else lib.vdec_demap_device
+    if fn(n, C.c_void_p(iq.data_ptr()), nsym, C.c_void_p(out.data_ptr()), C.c_void_p(s.cuda_stream)) != 0:
+        raise VdecError(_lib.last_error())
+    return out
+
+
+CHANNEL_AWGN, CHANNEL_AWGN_HARD, CHANNEL_BSC = 0, 1, 2
+
+
+def sweep(code: CodeParam, points, frames_per_batch: int, channel: int = CHANNEL_AWGN, parity: int = PARITY_REF, seed: int = 12345,
+          ndev: int = 0, devices=None, min_frame_errors: int = 0, max_frames: int = 0, chunk_frames: int = 0,
+          resume_path: Optional[str] = None, flags: int = 0):
+    """The C entry ``vdec_sweep``: the drivers' operating-point loop (AWGN-channel/main.c:193-234,
+    binary-symmetric-channel/main.c:147-176) on `ndev` GPUs of this node from ONE process (0 = all), counters summed
+    with ncclAllReduce.  points: Eb/N0 in dB, or crossover rates in ppm for CHANNEL_BSC.
+    Returns an int array [len(points)][3] = bits, bit errors, frame errors."""
+    lib = _lib.load()
+    cfg = make_config(code, HARD_U16 if channel == CHANNEL_BSC else SOFT_F32, parity, flags=flags)
+    sw = _lib.VdecSweepConfig(seed, frames_per_batch, max_frames, min_frame_errors, chunk_frames, channel,
+                              resume_path.encode() if resume_path else None)
+    pts = (C.c_double * len(points))(*[float(p) for p in points])
+    out = np.zeros((len(points), 3), np.uint64)
+    devs = (C.c_int * len(devices))(*devices) if devices else None
+    rc = lib.vdec_sweep(C.byref(cfg), C.byref(sw), pts, len(points), devs, len(devices) if devices else ndev,
+                        out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc != 0:
         raise VdecError(_lib.last_error())
     return out
 

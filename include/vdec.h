@@ -97,6 +97,8 @@ const char* vdec_config_kernel_name(const struct vdec_config* cfg);
  * device needed): returns the cubin size, 0 when the config is served without run-time compilation, -1 on failure
  * (vdec_last_error() has the compiler log). */
 long        vdec_jit_check(const struct vdec_config* cfg);
+/* same for the raw-I/Q variant of the register kernel (K <= 7 soft codes outside the registry); 0 = not applicable */
+long        vdec_jit_check_iq(const struct vdec_config* cfg);
 
 /* geometry */
 uint32_t    vdec_steps(const vdec_t* h);             /* T = L + K - 1 */
@@ -108,7 +110,11 @@ const char* vdec_kernel_name(const vdec_t* h);       /* which CUDA kernel family
 int         vdec_labels(const vdec_t* h, uint8_t* labels);
 
 /* decode `nframes` frames; buffers in device memory, asynchronous on `cuda_stream`
- * (a cudaStream_t, NULL = legacy default stream).  path_metric_dev may be NULL. */
+ * (a cudaStream_t, NULL = legacy default stream).  path_metric_dev may be NULL.
+ * Soft (float) inputs must be 16-byte aligned (checked: -1 otherwise).
+ * ONE CALL IN FLIGHT PER HANDLE: the survivor scratch and staging buffers belong to the handle, so the device entry
+ * points of one handle must all be issued on the same stream (or be separated by a synchronisation); concurrent
+ * streams need one handle each, as concurrent frames need one `struct decoder` each in the reference. */
 int vdec_decode_device(vdec_t* h, const void* in_dev, uint64_t nframes, uint8_t* out_dev,
                        int32_t* path_metric_dev, void* cuda_stream);
 /* same with HOST buffers: H2D, kernels, D2H, synchronous (pipelined in chunks).
@@ -122,6 +128,10 @@ int vdec_decode_host(vdec_t* h, const void* in_host, uint64_t nframes, uint8_t* 
  * bytes that cross PCIe per decoded bit (8.2 instead of 16.2 at K=7, n=2).  Soft metric only. */
 int vdec_decode_iq_device(vdec_t* h, const float* iq_dev, uint64_t nframes, uint8_t* out_dev, void* cuda_stream);
 int vdec_decode_iq_host(vdec_t* h, const float* iq_host, uint64_t nframes, uint8_t* out_host);
+/* Which kernels serve the raw-I/Q entry of this handle: the register kernels (K <= 7) form the branch metrics inside
+ * the decoder kernel's input feeder (one launch, 8 B of HBM per trellis step); other families run the demapper kernel
+ * into a staging buffer first.  Precondition of the fused form: I/Q finite, |I|, |Q| < 1e19. */
+const char* vdec_iq_kernel_name(vdec_t* h);
 /* Sliding-window decoding of ONE long or unterminated symbol stream (north_star piece 4).
  * The reference keeps the survivors of the whole frame (viterbi-decoder.c:183) and cannot do this.  The stream
  * of `nsteps` trellis steps (same per-step format as the batched input) is decoded as overlapping windows of
@@ -151,11 +161,18 @@ int vdec_count_errors_device(vdec_t* h, const uint8_t* decoded_dev, const uint8_
 int vdec_demap_device(uint32_t symlen_out, const float* iq_dev, uint64_t nsym, float* metrics_dev,
                       void* cuda_stream);
 
+/* hard demapper, bit-exact to common/hard-demapper.c:62-102: each point is snapped to the nearest constellation point
+ * (strict '<' on the squared distances: lowest index wins) and the soft demapper's expression is evaluated at the
+ * snapped point: iq [nsym][2] -> metrics [nsym][2^n] (the `*_h` curves of results/awgn_channel.m:16-28) */
+int vdec_hard_demap_device(uint32_t symlen_out, const float* iq_dev, uint64_t nsym, float* metrics_dev,
+                           void* cuda_stream);
+
 /* GPU-resident synthetic link for frames [first_frame, first_frame+nframes): counter-based
  * random payload -> encoder (encoder.c:84-119) -> mapper (mapper.c:54-71) -> AWGN of standard
  * deviation `sigma` per real dimension (main.c:100-102) -> demapper.  Random numbers depend only
  * on (seed, global frame index, step), so results do not depend on how frames are sharded.
- * payload_dev [nframes][(L+7)/8]; metrics_dev [nframes][T][M]; iq_dev (optional) [nframes][T][2]. */
+ * payload_dev [nframes][(L+7)/8]; metrics_dev [nframes][T][M] and iq_dev [nframes][T][2]: either may be NULL
+ * (not both); I/Q only is the cheap form, to be decoded through vdec_decode_iq_device. */
 int vdec_synth_awgn_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uint64_t seed, float sigma,
                            uint8_t* payload_dev, float* metrics_dev, float* iq_dev, void* cuda_stream);
 /* binary symmetric channel: each coded bit flipped with probability crossover_ppm/1e6
@@ -163,6 +180,36 @@ int vdec_synth_awgn_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, ui
 int vdec_synth_bsc_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uint64_t seed,
                           uint32_t crossover_ppm, uint8_t* payload_dev, uint8_t* symbols_dev,
                           void* cuda_stream);
+
+/* ---- the drivers' operating-point loop on all GPUs of the node, from C --------------------
+ * Replaces the Eb/N0 loop of AWGN-channel/main.c:193-234 and the crossover-rate loop of
+ * binary-symmetric-channel/main.c:147-176: per point, batches of `frames_per_batch` synthetic frames are split into
+ * contiguous ranges of the global frame index over `ndev` devices (single process, one stream per device), each
+ * device runs source -> channel -> [demapper ->] decoder -> error count on its range, and the three counters are
+ * summed with one ncclAllReduce(uint64, sum) per batch (NCCL is opened with dlopen; not needed for ndev = 1).
+ * A point ends after one batch, or — with min_frame_errors > 0 — once that many errored frames were seen or
+ * max_frames were simulated.  Results do not depend on ndev (data is keyed by the global frame index).
+ *   points[i]      Eb/N0 in dB (AWGN channels, sigma as main.c:153-161) or the crossover rate in ppm (BSC, main.c:103-109)
+ *   devices        CUDA ordinals, NULL = 0 .. ndev-1; ndev = 0: every device present
+ *   counters_out   [npoints][3] = bits compared, bit errors, frames in error (main.c:129-141)
+ * cfg->metric must be VDEC_SOFT_F32 for the AWGN channels and VDEC_HARD_U16 for the BSC; cfg->device is ignored. */
+enum vdec_channel {
+    VDEC_CHANNEL_AWGN = 0,        /* soft demapper (common/demapper.c), fused into the decoder where the kernel family allows */
+    VDEC_CHANNEL_AWGN_HARD = 1,   /* hard demapper (common/hard-demapper.c): the `*_h` curves */
+    VDEC_CHANNEL_BSC = 2          /* bit flips on the encoder output, hard-decision decoder */
+};
+struct vdec_sweep_config {
+    uint64_t seed;
+    uint64_t frames_per_batch;    /* frames per point and batch, all devices together */
+    uint64_t max_frames;          /* with min_frame_errors: give up on a point after this many frames (0 = no limit) */
+    uint64_t min_frame_errors;    /* 0 = one batch per point */
+    uint32_t chunk_frames;        /* frames per launch and device, 0 = 65536 */
+    uint32_t channel;             /* enum vdec_channel */
+    const char* resume_path;      /* optional: counters are appended here after every batch and picked up on restart */
+};
+int vdec_sweep(const struct vdec_config* cfg, const struct vdec_sweep_config* sweep, const double* points,
+               uint32_t npoints, const int* devices, int ndev, uint64_t* counters_out);
+int vdec_device_count(void);
 
 #ifdef __cplusplus
 }

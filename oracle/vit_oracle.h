@@ -11,7 +11,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this.  The CUDA library never links or calls it.
  *
- * Parity status: PINNED — tests/test_oracle_vs_reference.py checks this file
+ * Parity status: PINNED — tests/test_oracle.py checks this file
  * bit-for-bit against the unmodified reference objects (oracle/_ref, built by
  * oracle/Makefile from /root/reference) on every codebook code the reference
  * can run (K <= 8, L + K - 1 <= 255), and tests/golden/ holds vectors dumped

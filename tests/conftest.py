@@ -10,6 +10,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# the library's on-disk kernel cache is opt-in: the suite opts in with an in-tree directory (tools/prewarm_jit.py fills
+# it on the CPU at build time, so a GPU run does not spend minutes in NVRTC)
+os.environ.setdefault("VDEC_JIT_CACHE", os.path.join(ROOT, "build", "jit_cache"))
 
 
 def pytest_configure(config):

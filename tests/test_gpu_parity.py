@@ -60,7 +60,7 @@ def test_golden_vectors(cc, torch_cuda, path, flags):
 SOFT_CASES = [  # (code getter, L, frames, sigma)
     ("cb0", 40, 1000, 0.45), ("cb1", 40, 333, 0.5), ("cb2", 57, 129, 0.5), ("cb3", 40, 64, 0.45), ("cb5", 40, 257, 0.6),
     ("k7r12", 1024, 96, 0.446154216921401), ("k7r12", 249, 33, 0.56), ("k7r12", 5, 31, 0.4), ("k7r12", 1, 7, 0.4),
-    ("k7r13", 300, 65, 0.6), ("k9", 128, 9, 0.5), ("k15", 40, 2, 0.5),
+    ("k7r13", 300, 65, 0.6), ("k7r13", 1024, 70, 0.55), ("k9", 128, 9, 0.5), ("k15", 40, 2, 0.5),
     # lane-group register kernels (2, 4, 8, 16 lanes per frame), ragged frame counts and lengths
     ("k8", 200, 67, 0.5), ("k9", 1024, 41, 0.45), ("k9", 3, 5, 0.5), ("k10", 150, 13, 0.5), ("k11", 97, 7, 0.5),
     # register-tile kernels (4 .. 256 threads per frame): every window remainder T % 6, ragged frame counts
@@ -103,6 +103,7 @@ def test_soft_vs_oracle(cc, orc, torch_cuda, key, L, F, sigma, parity):
 HARD_CASES = [("cb0", 17000, 9, 0.05),      # too long for the shared-memory output tile: table-driven kernels
               ("cb0", 40, 1001, 0.0125), ("cb0", 40, 1000, 0.2), ("cb1", 40, 300, 0.05), ("cb3", 40, 100, 0.05),
               ("cb5", 40, 257, 0.1), ("k7r12", 249, 70, 0.05), ("k7r12", 1024, 40, 0.04), ("k7r13", 100, 33, 0.1),
+              ("k7r13", 1024, 45, 0.08),      # BASELINE config 3 at its own frame length
               ("k9", 100, 8, 0.05), ("k15", 30, 2, 0.03),
               # packed 16-bit register-tile kernels: odd frame counts, every window remainder, several pairs per warp / CTA
               ("k8", 200, 133, 0.05), ("k8", 3, 5, 0.1), ("k9", 1024, 77, 0.04), ("k9", 7, 300, 0.1), ("k11", 150, 21, 0.05),
@@ -279,6 +280,241 @@ def test_raw_iq_entry_matches_demapper_plus_decoder(cc, orc, torch_cuda):
     with pytest.raises(cc.VdecError):
         d = cc.BatchDecoder(cc.get_code(0), cc.HARD_U16)
         d.decode_iq_host(np.zeros((1, 42, 2), np.float32))
+
+
+def test_rate_one_codes(cc, orc, torch_cuda):
+    """symlen_out = 1 (one coded bit per step, a 2-point constellation): accepted by vdec_create, served by the
+    table-driven kernels; soft, hard and raw-I/Q entries against the oracle"""
+    for K, octal, L, F in ((3, "7", 40, 200), (5, "23", 100, 64), (7, "171", 64, 33), (9, "561", 30, 5)):
+        code = cc.CodeParam(1, K, L, (cc.codes.left_align(octal, K),))
+        for parity in (0, 1):
+            oc = ocode(code, parity)
+            _, met = make_soft_inputs(orc, oc, F, 0.7, seed=K * 10 + parity)
+            out, name = _decode_soft(cc, torch_cuda, code, parity, met)
+            assert name.startswith("generic"), name
+            assert np.array_equal(out, orc.decode_soft(oc, met)), name
+            _, sym = make_hard_inputs(orc, oc, F, 0.08, seed=K)
+            exp, exp_pm = orc.decode_hard(oc, sym)
+            o, pm, name = _decode_hard(cc, torch_cuda, code, parity, sym)
+            assert np.array_equal(o, exp) and np.array_equal(pm, exp_pm), name
+        dec = cc.BatchDecoder(code, cc.SOFT_F32, 1)
+        _, iq = dec.synth_awgn(F, 0, 5, 0.6, want_iq=True, want_metrics=False)
+        met = orc.demap(1, iq.cpu().numpy().reshape(-1, 2)).reshape(F, code.T, 2)
+        assert np.array_equal(dec.decode_iq(iq).cpu().numpy(), orc.decode_soft(ocode(code, 1), met))
+        dec.close()
+
+
+def test_quantised_mode_range_guard(cc, torch_cuda):
+    """VDEC_SOFT_U8 equals the reference's fp32 sums only while T * metric_max < 2^24: refused beyond"""
+    code = cc.codes.K7_R12.with_block_len(70000)
+    with pytest.raises(cc.VdecError):
+        cc.BatchDecoder(code, cc.SOFT_U8, 1, metric_max=255)
+    cc.BatchDecoder(code, cc.SOFT_U8, 1, metric_max=200).close()
+
+
+def test_fused_iq_entry_bit_exact(cc, orc, torch_cuda):
+    """Raw-I/Q entry of the register kernels: the branch metrics are formed in the decoder kernel's feeder with a
+    three-operation division (vdec_demap.cuh).  Bit-exactness of that shortcut is checked three ways: metrics of the
+    synthetic source (same shortcut) against the IEEE-division demapper kernel and the CPU demapper on a few million
+    points incl. exact constellation points and near-misses, and decoded bits against demapper + decoder."""
+    torch = torch_cuda
+    C = cc.codes
+    cases = [(C.K7_R12.with_block_len(1024), 0, 257), (C.K7_R12.with_block_len(333), 1, 100), (C.K7_R13.with_block_len(1024), 0, 70),
+             (C.K7_R13.with_block_len(50), 1, 300), (cc.get_code(0), 0, 1000), (cc.get_code(3), 0, 500), (cc.get_code(5), 0, 400),
+             (cc.CodeParam(2, 6, 77, (C.left_align("53", 6), C.left_align("75", 6))), 1, 90)]       # compiled at run time
+    for code, parity, F in cases:
+        oc = ocode(code, parity)
+        dec = cc.BatchDecoder(code, cc.SOFT_F32, parity)
+        assert "feeder" in dec.iq_kernel_name, dec.iq_kernel_name
+        for sigma in (0.0, 0.05, 0.6):
+            payload, met, iq = dec.synth_awgn(F, 17, 99, sigma, want_iq=True)
+            ref_met = cc.demap(code.n, iq)                                         # IEEE division
+            assert torch.equal(met.view(torch.int32), ref_met.view(torch.int32)), (code.name, sigma)
+            out = dec.decode_iq(iq)
+            assert torch.equal(out, dec.decode(met))
+            if sigma == 0.6:
+                cpu_met = orc.demap(code.n, iq.cpu().numpy().reshape(-1, 2)).reshape(F, code.T, code.M)
+                assert np.array_equal(met.cpu().numpy().view(np.uint32), cpu_met.view(np.uint32))
+                assert np.array_equal(out.cpu().numpy(), orc.decode_soft(oc, cpu_met))
+                assert np.array_equal(dec.decode_iq_host(iq.cpu().numpy()), out.cpu().numpy())
+        dec.close()
+    # the division shortcut over many magnitudes: points scaled from 1e-6 to 1e6 around the constellation
+    dec = cc.BatchDecoder(C.K7_R12.with_block_len(2042), cc.SOFT_F32, 0)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for n in (2, 3):
+        d3 = cc.BatchDecoder(C.K7_R13.with_block_len(2042), cc.SOFT_F32, 0) if n == 3 else dec
+        iq = torch.randn((512, 2048, 2), device="cuda", generator=g) * torch.logspace(-6, 6, 512, device="cuda")[:, None, None]
+        iq = iq.float().contiguous()
+        a = d3.decode_iq(iq)
+        b = d3.decode(cc.demap(n, iq))
+        assert torch.equal(a, b)
+        if n == 3:
+            d3.close()
+    dec.close()
+
+
+def test_hard_demapper_matches_reference_arithmetic(cc, orc, torch_cuda):
+    """common/hard-demapper.c:62-102 on the GPU: bit-equal to the oracle's restatement (itself bit-equal to the
+    compiled reference, tests/test_oracle.py), incl. points on decision boundaries (ties -> lowest index)"""
+    torch = torch_cuda
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3):
+        iq = (rng.standard_normal((200000, 2)) * 0.9).astype(np.float32)
+        iq[:1000] = 0.0                                     # equidistant from several points
+        iq[1000:2000, 0] = 0.0
+        iq[2000:3000, 1] = 0.0
+        iq[3000:4000] = orc.constellation(n)[rng.integers(0, 1 << n, 1000)]
+        got = cc.demap(n, torch.from_numpy(iq).cuda(), hard=True).cpu().numpy()
+        exp = orc.demap(n, iq, hard=True)
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), n
+
+
+@pytest.mark.parametrize("path", [p for p in golden_files("soft") if "harddemap" in p], ids=lambda p: p.split("/")[-1][:-4])
+def test_hard_demapped_golden_inputs_reproduced_on_gpu(cc, orc, torch_cuda, path):
+    """the compiled reference's hard-demapped decoder inputs carry their decoded outputs: the GPU decoder on those
+    metrics reproduces them (n = 3 metrics are non-integers: the fp32 kernels, not the quantised mode)"""
+    z, ocd = load_golden(path)
+    code = to_param(cc, ocd)
+    out, _ = _decode_soft(cc, torch_cuda, code, cc.PARITY_REF, z["inputs"])
+    assert np.array_equal(out, z["outputs"])
+
+
+PUBLISHED_HARD_DEMAP = {   # results/awgn_channel.m:16,19,25,28 (`*h` rows) — Eb/N0 = 0, 2, 4, 6 dB; block length 40
+    0: [0.40942000, 0.30961000, 0.14543500, 0.03102900],
+    1: [0.23225375, 0.12338125, 0.04132875, 0.00733887],
+    3: [0.26318250, 0.12922125, 0.03216750, 0.00354537],
+    5: [0.18751250, 0.08752625, 0.02753250, 0.00675150],
+}
+
+
+def _published_band(p, pub, pub_bits):
+    """our 95 % interval widened by the published run's own spread (it is a Monte-Carlo estimate too)"""
+    pub_frames = pub_bits / 40
+    pub_rel = 1.96 / max(1.0, (pub_frames * min(1.0, pub * 40 / 3)) ** 0.5)      # bursts of ~3 bit errors
+    return p["ci95_lo"] * (1 - pub_rel), p["ci95_hi"] * (1 + pub_rel)
+
+
+@pytest.mark.parametrize("idx", [0, 1, 3, 5])
+def test_hard_demapped_ber_curve_agrees_with_published_results(cc, torch_cuda, idx):
+    """the `*_h` curves: GPU source -> GPU hard demapper -> GPU decoder vs results/awgn_channel.m"""
+    code = cc.get_code(idx)
+    dec = cc.BatchDecoder(code, cc.SOFT_F32, cc.PARITY_REF)
+    pts = cc.sweep_awgn(dec, [0.0, 2.0, 4.0, 6.0], [200_000, 200_000, 400_000, 1_000_000], seed=77 + idx, hard_demap=True)
+    for p, pub in zip(pts, PUBLISHED_HARD_DEMAP[idx]):
+        assert p["frame_errors"] >= 100
+        lo, hi = _published_band(p, pub, 800_000 if p["ebn0_db"] <= 4.0 else 8_000_000)
+        assert lo <= pub <= hi, (idx, p, pub)
+    dec.close()
+
+
+PUBLISHED_BSC = {   # results/binary_symmetric_channel.m:5-13, 17 channel error rates, 8e8 bits each (8e7 / 8e6 / 8e5 above 1.25 % / 5 % / 20 %)
+    0: [0.000000, 0.000000, 0.000000, 0.000001, 0.000024, 0.000616, 0.002431, 0.009545, 0.014733, 0.035913, 0.120755, 0.227862, 0.298730, 0.445908, 0.480994, 0.493111, 0.493863],
+    1: [0.000000, 0.000000, 0.000002, 0.000010, 0.000051, 0.000330, 0.000848, 0.002472, 0.003602, 0.008331, 0.031064, 0.072438, 0.112608, 0.299624, 0.414149, 0.465758, 0.469379],
+    2: [0.000000, 0.000000, 0.000001, 0.000007, 0.000039, 0.000239, 0.000599, 0.001741, 0.002551, 0.006114, 0.026200, 0.069603, 0.115543, 0.326379, 0.430994, 0.472725, 0.475711],
+    3: [0.000000, 0.000000, 0.000001, 0.000002, 0.000013, 0.000093, 0.000270, 0.000962, 0.001532, 0.004366, 0.023669, 0.069840, 0.119863, 0.338624, 0.435971, 0.473404, 0.476187],
+    5: [0.000000, 0.000000, 0.000000, 0.000000, 0.000000, 0.000000, 0.000003, 0.000021, 0.000043, 0.000182, 0.001618, 0.006817, 0.015133, 0.120716, 0.290245, 0.413025, 0.422798],
+}
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3, 5])
+def test_bsc_ber_table_agrees_with_published_results(cc, torch_cuda, idx):
+    """the BSC driver's whole table (binary-symmetric-channel/main.c:103-109,147-176: 17 channel error rates) on the
+    GPU — source, bit flips, hard-decision decoder, error count — against results/binary_symmetric_channel.m:5-13.
+    The published values are printed with six decimals: compared inside our 95 % interval widened by the published
+    run's spread and by half a unit of the last printed digit."""
+    code = cc.get_code(idx)
+    dec = cc.BatchDecoder(code, cc.HARD_U16, cc.PARITY_REF)
+    rates = list(cc.BSC_RATES_PPM)
+    frames = [4_000_000 if r <= 3125 else 1_000_000 if r <= 50000 else 200_000 for r in rates]
+    pts = cc.sweep_bsc(dec, rates, frames, seed=31 + idx)
+    assert [p["crossover_ppm"] for p in pts] == rates
+    for p, pub, r in zip(pts, PUBLISHED_BSC[idx], rates):
+        pub_bits = 8e8 if r <= 12500 else 8e7 if r <= 50000 else 8e6 if r <= 200000 else 8e5
+        lo, hi = _published_band(p, max(pub, 1e-9), pub_bits) if p["frame_errors"] else (0.0, p["ci95_hi"])
+        assert lo - 0.6e-6 <= pub <= hi + 0.6e-6, (idx, r, p, pub)
+        if pub >= 1e-4:
+            assert p["frame_errors"] >= 50, (idx, r, p)
+    assert dec.kernel_name.startswith("regs2_hard_u16x2"), dec.kernel_name
+    dec.close()
+
+
+def test_c_sweep_entry_equals_python_sweep(cc, torch_cuda, tmp_path):
+    """vdec_sweep (C: single process, all devices, ncclAllReduce per batch) counts exactly what the Python sweep
+    counts — same data keyed by the global frame index — for the three channels, with adaptive stopping and resume"""
+    import torch
+    ndev = torch.cuda.device_count()
+    code = cc.get_code(3)
+    dec = cc.BatchDecoder(code, cc.SOFT_F32, cc.PARITY_REF)
+    grid = [1.0, 3.0, 5.0]
+    py = cc.sweep_awgn(dec, grid, 50_000, seed=5, chunk=20_000)
+    got = cc.sweep(code, grid, 50_000, cc.CHANNEL_AWGN, cc.PARITY_REF, seed=5, ndev=1, chunk_frames=20_000)
+    assert got.tolist() == [[p["bits"], p["bit_errors"], p["frame_errors"]] for p in py]
+    if ndev > 1:      # shard invariance through NCCL
+        assert cc.sweep(code, grid, 50_000, cc.CHANNEL_AWGN, cc.PARITY_REF, seed=5, ndev=0, chunk_frames=7_000).tolist() == got.tolist()
+    pyh = cc.sweep_awgn(dec, grid, 30_000, seed=6, hard_demap=True)
+    goth = cc.sweep(code, grid, 30_000, cc.CHANNEL_AWGN_HARD, cc.PARITY_REF, seed=6, ndev=1)
+    assert goth.tolist() == [[p["bits"], p["bit_errors"], p["frame_errors"]] for p in pyh]
+    # adaptive stopping: batches until 300 errored frames or 10 batches, identical in both drivers
+    pya = cc.sweep_awgn(dec, [4.0, 7.0], 20_000, seed=9, min_frame_errors=300, max_frames=200_000)
+    resume = str(tmp_path / "sweep.resume")
+    gota = cc.sweep(code, [4.0, 7.0], 20_000, cc.CHANNEL_AWGN, cc.PARITY_REF, seed=9, ndev=1, min_frame_errors=300,
+                    max_frames=200_000, resume_path=resume)
+    assert gota.tolist() == [[p["bits"], p["bit_errors"], p["frame_errors"]] for p in pya]
+    # a restart with the resume file does no work and returns the same counters
+    again = cc.sweep(code, [4.0, 7.0], 20_000, cc.CHANNEL_AWGN, cc.PARITY_REF, seed=9, ndev=1, min_frame_errors=300,
+                     max_frames=200_000, resume_path=resume)
+    assert again.tolist() == gota.tolist()
+    dec.close()
+    hd = cc.BatchDecoder(cc.get_code(0), cc.HARD_U16, cc.PARITY_REF)
+    pyb = cc.sweep_bsc(hd, [12500, 50000], 100_000, seed=8)
+    gotb = cc.sweep(cc.get_code(0), [12500, 50000], 100_000, cc.CHANNEL_BSC, cc.PARITY_REF, seed=8, ndev=1)
+    assert gotb.tolist() == [[p["bits"], p["bit_errors"], p["frame_errors"]] for p in pyb]
+    hd.close()
+    with pytest.raises(cc.VdecError):
+        cc.sweep(cc.get_code(0), [1.0], 10, cc.CHANNEL_BSC + 1)
+
+
+def test_stream_decode_falls_back_when_the_window_breaks_packed_limits(cc, orc, torch_cuda):
+    """handles whose block_len selected a packed 16-bit kernel, streamed with windows beyond that kernel's range
+    (T * metric_max >= 2^14, or more than 6400 steps of shared-memory tile): the call must still be exact"""
+    torch = torch_cuda
+    code = cc.codes.K7_R12.with_block_len(64)
+    big = cc.codes.K7_R12.with_block_len(30000)
+    # hard decisions, small-L handle (regs2), window 8192 > 6400 steps
+    hd = cc.BatchDecoder(code, cc.HARD_U16, 1)
+    assert hd.kernel_name.startswith("regs2_hard_u16x2")
+    ref_dec = cc.BatchDecoder(big, cc.HARD_U16, 1)
+    _, sym = ref_dec.synth_bsc(1, 0, 3, 30000)
+    full, _ = ref_dec.decode(sym)
+    x = sym.reshape(-1)
+    for blk, dep in ((1024, 128), (7168, 512)):
+        got = hd.decode_stream(x, blk, dep, start_known=True)
+        assert torch.equal(got[: big.L // 8], full[0, : big.L // 8]), (blk, dep)
+    hd.close(); ref_dec.close()
+    # quantised soft, small-L handle with metric_max = 200: windows of 1536 steps overflow 16 bits
+    qd = cc.BatchDecoder(code, cc.SOFT_U8, 1, metric_max=200)
+    assert qd.kernel_name.startswith("regs2_soft_u8x2"), qd.kernel_name
+    sd = cc.BatchDecoder(big, cc.SOFT_F32, 1)
+    _, met = sd.synth_awgn(1, 0, 4, cc.awgn_sigma(3.0))
+    q = torch.clamp(torch.round(met * 60.0), max=200).to(torch.uint8).contiguous()
+    full = sd.decode(q.float())
+    got = qd.decode_stream(q.reshape(-1, 4), 1024, 256, start_known=True)
+    assert torch.equal(got[: big.L // 8], full[0, : big.L // 8])
+    qd.close(); sd.close()
+
+
+def test_misaligned_soft_input_is_refused(cc, torch_cuda):
+    torch = torch_cuda
+    code = cc.codes.K7_R12.with_block_len(10)
+    dec = cc.BatchDecoder(code, cc.SOFT_F32, 0)
+    buf = torch.zeros((2 * code.T * code.M + 1,), dtype=torch.float32, device="cuda")
+    import ctypes as C
+    out = torch.empty((2, dec.out_bytes), dtype=torch.uint8, device="cuda")
+    rc = dec.lib.vdec_decode_device(dec.h, C.c_void_p(buf.data_ptr() + 4), 2, C.c_void_p(out.data_ptr()), None, None)
+    assert rc == -1
+    rc = dec.lib.vdec_decode_device(dec.h, C.c_void_p(buf.data_ptr()), 2, C.c_void_p(out.data_ptr()), None, None)
+    assert rc == 0
+    dec.sync(); dec.close()
 
 
 PUBLISHED_SOFT = {   # results/awgn_channel.m:15,18,24,27 — Eb/N0 = 0, 2, 4, 6 dB; block length 40

@@ -84,6 +84,9 @@ def test_unregistered_polynomials_compile_at_run_time(cc):
     assert cc.jit_check(k7, cc.SOFT_F32, cc.PARITY_LINEAR, cc.NO_JIT) == 0
     assert cc.jit_check(k7, cc.SOFT_F32, cc.PARITY_LINEAR) > 10000                  # a cubin came back
     assert cc.jit_check(k6r3, cc.HARD_U16, cc.PARITY_LINEAR) > 10000
+    assert cc.jit_check(k7, cc.SOFT_F32, cc.PARITY_LINEAR, iq=True) > 10000         # raw-I/Q variant: demapper in the feeder
+    assert cc.jit_check(k6r3, cc.SOFT_F32, cc.PARITY_REF, iq=True) > 10000
+    assert cc.jit_check(k9, cc.SOFT_F32, cc.PARITY_LINEAR, iq=True) == 0            # tile kernels take staged metrics
     assert cc.jit_check(k9, cc.SOFT_F32, cc.PARITY_REF) > 10000
     # rate 1/3 on a large trellis: no tile kernel model, stays table-driven
     k9r3 = CodeParam(3, 9, 100, (left_align("557", 9), left_align("663", 9), left_align("711", 9)))
@@ -144,6 +147,8 @@ def test_library_refuses_without_gpu(cc):
     leg = cc.LegacyDecoder("awgn")
     assert leg.init(cc.get_code(0)) == -1                   # decoder_init reports failure, no CPU fallback
     assert leg.input(np.zeros(4, np.float32)) == -1
+    with pytest.raises(cc.VdecError, match="no CUDA device"):      # the C sweep entry neither
+        cc.sweep(cc.get_code(0), [2.0], 100)
 
 
 def test_product_never_imports_oracle():

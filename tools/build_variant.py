@@ -30,7 +30,7 @@ def comp(n):
 
 
 with cf.ThreadPoolExecutor(8) as ex:
-    objs = list(ex.map(comp, ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_tile2.cu", "vdec_generic.cu", "vdec_synth.cu",
+    objs = list(ex.map(comp, ["vdec_api.cu", "vdec_regs.cu", "vdec_regs2.cu", "vdec_regsw.cu", "vdec_tile.cu", "vdec_tile2.cu", "vdec_generic.cu", "vdec_synth.cu", "vdec_sweep.cu",
                               "vdec_jit.cu"]))
 subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", os.path.join(out, "libvdec.so"), *objs,
                 "-Xlinker", "-Bsymbolic", "-ldl"], check=True)

@@ -48,6 +48,21 @@ def main():
     dec.decode_stream(x.reshape(-1, code.M), 256, 64, start_known=True)
     torch.cuda.synchronize()
     print("ok stream", flush=True)
+    # raw-I/Q entry (demapper in the feeder), I/Q-only source, hard demapper, the C sweep entry
+    for code, parity, F in ((C.K7_R12.with_block_len(61), cc.PARITY_REF, 45), (C.K7_R13.with_block_len(35), cc.PARITY_LINEAR, 33),
+                            (cc.get_code(5), cc.PARITY_REF, 70)):
+        d = cc.BatchDecoder(code, cc.SOFT_F32, parity)
+        _, iq = d.synth_awgn(F, 3, 1, cc.awgn_sigma(3.0), want_iq=True, want_metrics=False)
+        oc = oracle.Code(code.n, code.K, code.L, code.polynomials, parity)
+        met = orc.demap(code.n, iq.cpu().numpy().reshape(-1, 2)).reshape(F, code.T, code.M)
+        assert np.array_equal(d.decode_iq(iq).cpu().numpy(), orc.decode_soft(oc, met)), d.iq_kernel_name
+        hm = cc.demap(code.n, iq, hard=True)
+        assert np.array_equal(hm.cpu().numpy().view(np.uint32), orc.demap(code.n, iq.cpu().numpy().reshape(-1, 2), hard=True).reshape(hm.shape).view(np.uint32))
+        print("ok", d.iq_kernel_name, flush=True)
+        d.close()
+    got = cc.sweep(cc.get_code(3), [3.0], 600, cc.CHANNEL_AWGN, cc.PARITY_REF, seed=2, ndev=1, chunk_frames=256)
+    assert int(got[0][0]) == 600 * 40
+    print("ok sweep", got.tolist(), flush=True)
 
 
 if __name__ == "__main__":

@@ -27,15 +27,22 @@ enum { OP_FADD, OP_FADD2, OP_FMNMX, OP_IADD, OP_IMAD, OP_SHF, OP_LOP, OP_SETPSEL
        MIX_F2_FADD,   // FADD2 : FADD 1:1
        OP_VIADDMNMX, OP_PRMT, OP_IADD3_3, MIX_VAM_IADD3, MIX_VAM_LOP, MIX_VAM_IMAD, MIX_PACKED,   // packed 16-bit recipe (vdec_regs2.cuh)
        MIX_FSETP_PFADD, MIX_ISETP_PFADD, MIX_ISETP_FMNMX, MIX_FSETP_FMNMX, MIX_ACS_I, MIX_ACS_FS,   // float vs integer compare for the decision
+       OP_FMULSAT,      // mul.sat.f32 by -INF: decision indicator (1.0 / 0.0) on the FMA pipes
+       OP_FFMA2,        // fma.rn.f32x2 (demapper arithmetic, packed)
+       OP_MOV,          // register moves (operand-pair building)
+       MIX_ACS_SIGN,    // the product recipe since round 1: 6 FADD2 + 4 FMNMX + 2 PRMT + 2 LOP3 per 4 state updates
+       MIX_ACS_SIGN_SAT,// same with one of the two decision pairs taken through FMUL.SAT + FFMA instead of PRMT + LOP3
        NOPS };
 static const char* names[NOPS] = {"FADD", "FADD2", "FMNMX", "IADD3", "IMAD", "SHF", "LOP3", "FSETP+SELP",
   "FADD+FMNMX", "FADD+IADD3", "FADD+IMAD", "FMNMX+IADD3",
   "ACS_A 2FADD+FMNMX+IADD+SHF", "ACS_B 2FADD+FSETP+SELP+@pOR", "ACS_C FADD2+2(FMNMX+IADD+SHF)",
   "ACS_D FADD2+2(FMNMX+FADDdiff+SHF)", "ACS_E FADD2+2(FMNMX+IMADdiff+SHF)", "ACS_F 2FADD+FMNMX+FADDdiff+SHF", "FADD2+FMNMX 1:1", "FADD2+2FMNMX", "FADD2+FADD 1:1",
   "VIADDMNMX.U16x2", "PRMT", "IADD3 (3-input)", "VIADDMNMX+IADD3", "VIADDMNMX+LOP3", "VIADDMNMX+IMAD", "PACKED 2ADD+2VIADDMNMX+2IADD3+PRMT+LOP3",
-  "FSETP+@pFADD", "ISETP+@pFADD", "ISETP+@pFADD+FMNMX", "FSETP+@pFADD+FMNMX", "ACS_I FADD2+2(ISETP+FMNMX+@pFADD)", "ACS_FS FADD2+2(FSETP+FMNMX+@pFADD)"};
+  "FSETP+@pFADD", "ISETP+@pFADD", "ISETP+@pFADD+FMNMX", "FSETP+@pFADD+FMNMX", "ACS_I FADD2+2(ISETP+FMNMX+@pFADD)", "ACS_FS FADD2+2(FSETP+FMNMX+@pFADD)",
+  "FMUL.SAT", "FFMA2", "MOV", "ACS_SIGN 6FADD2+4FMNMX+2PRMT+2LOP3 (4 updates)", "ACS_SIGN_SAT 6FADD2+4FMNMX+PRMT+LOP3+2FMUL.SAT+2FFMA (4 updates)"};
 // instructions per chain-iteration for each op
-static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5, 2, 3, 2, 2, 2, 2, 2, 2, 2, 8, 2, 2, 3, 3, 7, 7};
+static const int ipc_n[NOPS] = {2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 5, 5, 7, 7, 7, 5, 2, 3, 2, 2, 2, 2, 2, 2, 2, 8, 2, 2, 3, 3, 7, 7,
+                                2, 2, 2, 14, 16};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, long long* cyc) {
@@ -128,6 +135,42 @@ __global__ void __launch_bounds__(1024) k(float* out, float cf, uint32_t cu, lon
         asm volatile("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(p) : "r"(t0), "r"(t1));
         asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(((uint32_t*)&d[i])[0]) : "r"(p), "r"(cu));
         u[i] = n0; v[i] = n1;
+      }
+      if (OP == OP_FMULSAT) { asm volatile("mul.sat.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(g[i])); asm volatile("mul.sat.f32 %0, %0, %1;" : "+f"(g[i]) : "f"(f[i])); }
+      if (OP == OP_FFMA2) { asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(d[i]) : "l"(c2)); asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(c2) : "l"(d[i])); }
+      if (OP == OP_MOV) { asm volatile("mov.b32 %0, %1;" : "=r"(u[i]) : "r"(v[(i + 1) % NCH])); asm volatile("mov.b32 %0, %1;" : "=r"(v[i]) : "r"(u[(i + 3) % NCH])); }
+      if (OP == MIX_ACS_SIGN || OP == MIX_ACS_SIGN_SAT) {
+        // two register pairs (d[i], e) in, two out: candidates e/o/f/p, differences, minima, survivor bits
+        unsigned long long e, o, ff, pp, de, df;
+        const unsigned long long q2 = ((unsigned long long)__float_as_uint(g[i]) << 32) | __float_as_uint(f[i]);
+        asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(e) : "l"(d[i]), "l"(c2));
+        asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(o) : "l"(q2), "l"(c2));
+        asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(ff) : "l"(d[i]), "l"(q2));
+        asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(pp) : "l"(q2), "l"(d[i]));
+        asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(de) : "l"(o), "l"(e));
+        asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(df) : "l"(pp), "l"(ff));
+        float n0, n1, n2, n3;
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(n0) : "f"(__uint_as_float((uint32_t)e)), "f"(__uint_as_float((uint32_t)o)));
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(n1) : "f"(__uint_as_float((uint32_t)(e >> 32))), "f"(__uint_as_float((uint32_t)(o >> 32))));
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(n2) : "f"(__uint_as_float((uint32_t)ff)), "f"(__uint_as_float((uint32_t)pp)));
+        asm volatile("min.f32 %0, %1, %2;" : "=f"(n3) : "f"(__uint_as_float((uint32_t)(ff >> 32))), "f"(__uint_as_float((uint32_t)(pp >> 32))));
+        uint32_t p;
+        asm volatile("prmt.b32 %0, %1, %2, 0xFB00;" : "=r"(p) : "r"((uint32_t)de), "r"((uint32_t)(de >> 32)));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(u[i]) : "r"(p), "r"(cu));
+        if (OP == MIX_ACS_SIGN) {
+          asm volatile("prmt.b32 %0, %1, %2, 0xFB00;" : "=r"(p) : "r"((uint32_t)df), "r"((uint32_t)(df >> 32)));
+          asm volatile("lop3.b32 %0, %0, %1, %2, 0xf8;" : "+r"(v[i]) : "r"(p), "r"(cu));
+        } else {
+          float s0, s1; const float ninf = __int_as_float(0xff800000);
+          asm volatile("mul.sat.f32 %0, %1, %2;" : "=f"(s0) : "f"(__uint_as_float((uint32_t)df)), "f"(ninf));
+          asm volatile("mul.sat.f32 %0, %1, %2;" : "=f"(s1) : "f"(__uint_as_float((uint32_t)(df >> 32))), "f"(ninf));
+          float acc = __uint_as_float(v[i]);
+          asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc) : "f"(s0), "f"(cf));
+          asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(acc) : "f"(s1), "f"(cf));
+          v[i] = __float_as_uint(acc);
+        }
+        d[i] = ((unsigned long long)__float_as_uint(n1) << 32) | __float_as_uint(n0);
+        f[i] = n2; g[i] = n3;
       }
       if (OP == MIX_FSETP_PFADD) asm volatile("{.reg .pred p; setp.lt.f32 p, %1, %2; @p add.f32 %0, %0, %2;}" : "+f"(f[i]) : "f"(g[i]), "f"(cf));
       if (OP == MIX_ISETP_PFADD) asm volatile("{.reg .pred p; setp.lt.u32 p, %1, %2; @p add.f32 %0, %0, %3;}" : "+f"(f[i]) : "r"(u[i]), "r"(v[i]), "f"(cf));
