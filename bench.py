@@ -341,11 +341,12 @@ def run_gpu(args) -> int:
     # ---- GPU-resident link (config 5's inner loop): source -> channel (raw I/Q) -> demapper+decoder -> error count
     Fl = min(F, 1 << 19)
     lcount = torch.zeros(3, dtype=torch.int64, device=dev)
+    lout = torch.empty((Fl, dec.out_bytes), dtype=torch.uint8, device=dev)
 
     def link_step():
         pl, iq = dec.synth_awgn(Fl, rank * F, SEED + 1, sigma, want_iq=True, want_metrics=False)
-        o = dec.decode_iq(iq, out=out[:Fl])
-        dec.count_errors(o, pl, lcount)
+        dec.decode_iq(iq, out=lout)
+        dec.count_errors(lout, pl, lcount)
 
     link_ms = time_decode(torch, link_step, reps=3, warm=1)
     tl = torch.tensor([link_ms], dtype=torch.float64, device=dev)

@@ -23,6 +23,9 @@ using T11R = TileDef<11, 0x9BA0000000000000ull, 0xF620000000000000ull, true>;
 using T13R = TileDef<13, 0x8AD8000000000000ull, 0xFD88000000000000ull, true>;
 using T15R = TileDef<15, 0x99A2000000000000ull, 0xA572000000000000ull, true>;
 
+// rate 1/3 on a large trellis: K = 9 (557,663,711)_8, true-parity labels
+using T9N3 = TileDef<9, 0xB780000000000000ull, 0xD980000000000000ull, false, VDEC_TILE_VB, 3, 0xE480000000000000ull>;
+
 static const TileEntry* entries(int* count) {
     static const TileEntry e[] = {
         make_tile_entry<T8>("tile_soft_f32<K8 (371,247) linear, 2 threads/frame>"),
@@ -38,6 +41,7 @@ static const TileEntry* entries(int* count) {
         make_tile_entry<T11R>("tile_soft_f32<K11 (2335,3661) ref-labels, 16 threads/frame>"),
         make_tile_entry<T13R>("tile_soft_f32<K13 (10533,17661) ref-labels, 64 threads/frame>"),
         make_tile_entry<T15R>("tile_soft_f32<K15 (46321,51271) ref-labels, 256 threads/frame>"),
+        make_tile_entry<T9N3>("tile_soft_f32<K9 r1/3 (557,663,711) linear, 4 threads/frame>"),
     };
     *count = (int)(sizeof(e) / sizeof(e[0]));
     return e;

@@ -50,12 +50,16 @@ VDEC_HD constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return
 #endif
 VDEC_HD constexpr bool tile_thread_major(uint32_t tpf) { return tpf >= VDEC_TILE_TM_MIN && tpf <= VDEC_TILE_TM_MAX; }
 
-template <int K_, uint64_t P0_, uint64_t P1_, bool REF_ = false, int VB_ = (K_ == 8 ? 1 : VDEC_TILE_VB)>
+// N_ = 3 (rate 1/3, 8 metrics per step, third polynomial P2_): true-parity labels only — the de-facto labelling would
+// need a 64-letter extended alphabet.
+template <int K_, uint64_t P0_, uint64_t P1_, bool REF_ = false, int VB_ = (K_ == 8 ? 1 : VDEC_TILE_VB), int N_ = 2, uint64_t P2_ = 0>
 struct TileDef {
     static constexpr bool REF = REF_;                        // the reference's de-facto (non-linear) parity, vdec_labels.h
-    static constexpr int ML = REF_ ? 16 : 4;                 // size of the LINEAR label alphabet the kernel works in
+    static constexpr int K = K_, N = N_, M = 1 << N_, B = K_ - 1, S = 1 << (K_ - 1), TB = B - 6, TPF = 1 << TB;
+    static constexpr int ML = REF_ ? 16 : M;                 // size of the LINEAR label alphabet the kernel works in
     static constexpr int VB = VB_, VEC = 1 << VB_;           // registers a reader fetches per LDS (4: LDS.128)
-    static constexpr int K = K_, N = 2, M = 4, B = K_ - 1, S = 1 << (K_ - 1), TB = B - 6, TPF = 1 << TB;
+    static constexpr int kStepBytes = M * 4;                 // input bytes per trellis step
+    static_assert(N_ == 2 || (N_ == 3 && !REF_), "rate 1/2 (both label modes) or rate 1/3 with true-parity labels");
     static_assert(K_ >= 8 && K_ <= 15, "register-tile kernel covers K = 8 .. 15");
     static_assert(K_ > 8 || VB_ <= 1, "K = 8: the reader's second register bit is a register bit of the writer too, so at most 2 registers per LDS");
     static constexpr int FPC = kTileThreads / TPF;            // frames per CTA
@@ -67,10 +71,13 @@ struct TileDef {
     static constexpr int NREG = kTileThreads / RT;            // exchange regions per CTA
 
     // label contribution of logical state bit k (0 = oldest register bit) and of the input bit, P0 in the MSB
-    VDEC_HD static constexpr uint32_t gbit(int k) {
-        return (uint32_t)((((P0_ >> (64 - K_ + k)) & 1ull) << 1) | ((P1_ >> (64 - K_ + k)) & 1ull));
+    VDEC_HD static constexpr uint32_t taps(int pos) {                           // bit `pos` of every polynomial, P0 first
+        uint32_t x = (uint32_t)((((P0_ >> pos) & 1ull) << 1) | ((P1_ >> pos) & 1ull));
+        if (N_ == 3) x = (x << 1) | (uint32_t)((P2_ >> pos) & 1ull);
+        return x;
     }
-    VDEC_HD static constexpr uint32_t gin() { return (uint32_t)((((P0_ >> 63) & 1ull) << 1) | ((P1_ >> 63) & 1ull)); }
+    VDEC_HD static constexpr uint32_t gbit(int k) { return taps(64 - K_ + k); }
+    VDEC_HD static constexpr uint32_t gin() { return taps(63); }
     // De-facto labels (vdec_labels.h: parity_bit): bit j of the label is forced to 0 when z_j = XOR of the tapped
     // register bits at positions 4 mod 8 of the 64-bit shift register is set.  z is linear in the state too, so
     // the kernel carries the 4-bit LINEAR extended label el = parity | z << 2 and maps it to the metric index
@@ -81,7 +88,7 @@ struct TileDef {
         return gbit(k);
     }
     VDEC_HD static constexpr uint32_t ebit(int k) { return gbit(k) | (zbit(k) << 2); }
-    VDEC_HD static constexpr uint32_t metric_index(uint32_t el) { return (el & 3u) & ~(el >> 2); }
+    VDEC_HD static constexpr uint32_t metric_index(uint32_t el) { return REF_ ? ((el & 3u) & ~(el >> 2)) : el; }
     VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {          // the n-bit label the decoder compares against
         uint32_t x = i ? gin() : 0u;
         for (int k = 0; k < B; ++k) if ((s >> k) & 1u) x ^= ebit(k);
@@ -171,7 +178,7 @@ struct TileDef {
 // u = rotr6(register, k) is true logical bit c for c <= 5-k and bit B-6+c above (the bits that wrapped).
 template <class TD, int KS>
 struct TileCode {
-    static constexpr int K = 7, N = 2, B = 6, S = 64, M = TD::ML, NW = 2;
+    static constexpr int K = 7, N = TD::N, B = 6, S = 64, M = TD::ML, NW = 2;
     static constexpr bool kSignDecisions = TD::kSign;                          // the traceback kernel is told (TileShape::sign)
     VDEC_HD static constexpr uint32_t label(uint32_t u, uint32_t i) {          // register part of the (extended) label
         uint32_t x = i ? TD::gin() : 0u;
@@ -209,7 +216,7 @@ __device__ __forceinline__ void tile_get_pairs(uint32_t slot, uint32_t xt, uint6
 }
 
 constexpr int kTileRingGroups = 3;                                  // windows of input resident per frame
-constexpr int kTileRingBytes = kTileRingGroups * 6 * 16;            // per frame
+VDEC_HD constexpr int tile_ring_bytes(int n) { return kTileRingGroups * 6 * (4 << n); }     // per frame
 constexpr int kTileVmBytes = 6 * 16 * 4;                            // per frame: one window of metrics expanded by extended label
 
 template <class TD>
@@ -219,6 +226,7 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
     constexpr int B = TD::B, S = TD::S, TB = TD::TB, TPF = TD::TPF, FPC = TD::FPC, RT = TD::RT;
     extern __shared__ __align__(1024) unsigned char s_raw[];
     float* xall = reinterpret_cast<float*>(s_raw);                               // [NREG][RT * 64] exchange regions
+    constexpr int SB = TD::kStepBytes, GB = 6 * SB, kTileRingBytes = tile_ring_bytes(TD::N);
     unsigned char* rings = s_raw + (size_t)kTileThreads * 64 * 4;               // [FPC][kTileRingBytes]
     // REF: metrics expanded by extended label, [warp or frame][6 steps][16 labels][FPW frames of the warp] floats —
     // frames interleaved innermost so that the lanes of a warp spread over the banks; aligned for XOR addressing
@@ -246,23 +254,26 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
         xt[k] = x;
     }
 
-    // input ring of this frame: [group][step][4 floats], filled by the frame's thread 0
+    // input ring of this frame: [group][step][M floats], filled by the frame's thread 0
     const uint32_t ring = (uint32_t)__cvta_generic_to_shared(rings + (size_t)fic * kTileRingBytes);
     [[maybe_unused]] const uint32_t fiw = fic & (FPW - 1);                       // frame within its vm group
     [[maybe_unused]] float* vm = reinterpret_cast<float*>(vms + (size_t)(fic >> FSH) * FPW * kTileVmBytes) + fiw;
     [[maybe_unused]] const uint32_t vma = (uint32_t)__cvta_generic_to_shared(vm);
-    const float* nextp = in + (size_t)fr * stride_steps * 4;
+    const float* nextp = in + (size_t)fr * stride_steps * TD::M;
     uint32_t next_t = 0, woff = 0, roff = 0;
     auto prefetch = [&]() {
         if (tau == 0) {
 #pragma unroll
             for (int s = 0; s < 6; ++s)
-                if (next_t + s < T)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + woff + s * 16), "l"(nextp + s * 4) : "memory");
+                if (next_t + s < T) {
+#pragma unroll
+                    for (int c = 0; c < SB / 16; ++c)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(ring + woff + s * SB + c * 16), "l"(nextp + s * TD::M + c * 4) : "memory");
+                }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        nextp += 24; next_t += 6;
-        woff = (woff == (kTileRingGroups - 1) * 96) ? 0u : woff + 96;
+        nextp += 6 * TD::M; next_t += 6;
+        woff = (woff == (kTileRingGroups - 1) * GB) ? 0u : woff + GB;
     };
     prefetch();
     prefetch();
@@ -296,7 +307,7 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
         uint64_t bp[CD::M * CD::M];
         uint32_t dw[2];
         if constexpr (TD::REF) tile_get_pairs<CD, KS, 2 + FSH>(vma + KS * (64 << FSH), xt[KS], bp);
-        else tile_get_pairs<CD, KS>(ring + roff + KS * 16, xt[KS], bp);
+        else tile_get_pairs<CD, KS>(ring + roff + KS * SB, xt[KS], bp);
         acs_step_f2<CD, KS>(rp, bp, dw);
         if (live) sv[TD::kThreadMajor ? (size_t)(t + KS) : (size_t)(t + KS) * TPF] = make_uint2(dw[0], dw[1]);
     };
@@ -304,7 +315,7 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
     for (; t + 6 < T; t += 6) {
         begin_window();
         static_for<0, 6>(step);
-        roff = (roff == (kTileRingGroups - 1) * 96) ? 0u : roff + 96;
+        roff = (roff == (kTileRingGroups - 1) * GB) ? 0u : roff + GB;
         // ---- transpose: sigma' = rotr(sigma, 6) -------------------------------------------------------
         static_for<0, 64>([&](auto ac) {
             constexpr uint32_t A = decltype(ac)::value, c = TD::cw(A), cx = c & TD::wmask(), cd = c & ~TD::wmask();
@@ -423,10 +434,11 @@ struct TileShape {
     uint32_t B, TPF, FPC;
     bool ref;
     bool sign;              // survivor bits in the rotated layout of the sign-based decisions (TileDef::kSign)
+    uint32_t n;             // coded bits per step: input ring bytes
 };
-inline TileShape tile_shape(uint32_t K, bool ref) {
+inline TileShape tile_shape(uint32_t K, bool ref, uint32_t n = 2) {
     const uint32_t tpf = 1u << (K - 7);
-    return TileShape{K - 1, tpf, (uint32_t)kTileThreads / tpf, ref, K >= 9};
+    return TileShape{K - 1, tpf, (uint32_t)kTileThreads / tpf, ref, K >= 9, n};
 }
 inline size_t tile_surv_bytes_tpf(const LaunchGeom& g, uint32_t tpf) {
     return (size_t)g.nframes * g.T * tpf * sizeof(uint2) + (size_t)g.nframes * sizeof(uint32_t);
@@ -437,7 +449,7 @@ inline int tile_launch_kernel(const void* kern, const TileShape& sh, const Launc
                               uint32_t* scratch, cudaStream_t st) {
     uint2* surv = reinterpret_cast<uint2*>(scratch);
     uint32_t* final_state = reinterpret_cast<uint32_t*>(surv + (size_t)g.nframes * g.T * sh.TPF);
-    const size_t smem = (size_t)kTileThreads * 64 * 4 + (((size_t)sh.FPC * kTileRingBytes + 511) & ~(size_t)511) +
+    const size_t smem = (size_t)kTileThreads * 64 * 4 + (((size_t)sh.FPC * tile_ring_bytes((int)sh.n) + 511) & ~(size_t)511) +
                         (sh.ref ? (size_t)sh.FPC * kTileVmBytes : 0) + (kTileThreads / 32) * 8;
     VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (g.nframes + sh.FPC - 1) / sh.FPC;
@@ -461,7 +473,7 @@ size_t tile_surv_bytes(const LaunchGeom& g) { return tile_surv_bytes_tpf(g, TD::
 template <class TD>
 int tile_launch(const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st) {
     return tile_launch_kernel(reinterpret_cast<const void*>(&vit_tile_forward<TD>),
-                              TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF, TD::kSign}, g, in, out, scratch, st);
+                              TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF, TD::kSign, (uint32_t)TD::N}, g, in, out, scratch, st);
 }
 
 struct TileEntry {
@@ -486,16 +498,19 @@ TileEntry make_tile_entry(const char* name) {
 
 // Labels of the kernel's label model (TileDef::label) for run-time polynomials: a run-time compiled kernel serves a
 // request only when this equals the table computed from the caller's polynomials (vdec_labels.h).
-inline void tile_model_labels(uint32_t K, uint64_t p0, uint64_t p1, bool ref, uint8_t* labels) {
+inline void tile_model_labels(uint32_t K, uint64_t p0, uint64_t p1, bool ref, uint8_t* labels, uint32_t n = 2, uint64_t p2 = 0) {
     const uint32_t B = K - 1, S = 1u << B;
-    auto gbit = [&](int k) { return (uint32_t)((((p0 >> (64 - K + k)) & 1ull) << 1) | ((p1 >> (64 - K + k)) & 1ull)); };
-    auto ebit = [&](int k) { const int pos = 64 - (int)K + k; return gbit(k) | ((ref && (pos & 7) == 4) ? gbit(k) << 2 : 0u); };
-    const uint32_t gin = (uint32_t)((((p0 >> 63) & 1ull) << 1) | ((p1 >> 63) & 1ull));
+    auto taps = [&](int pos) {
+        uint32_t x = (uint32_t)((((p0 >> pos) & 1ull) << 1) | ((p1 >> pos) & 1ull));
+        return n == 3 ? ((x << 1) | (uint32_t)((p2 >> pos) & 1ull)) : x;
+    };
+    auto ebit = [&](int k) { const int pos = 64 - (int)K + k; return taps(pos) | ((ref && (pos & 7) == 4) ? taps(pos) << 2 : 0u); };
+    const uint32_t gin = taps(63);
     for (uint32_t s = 0; s < S; ++s)
         for (uint32_t i = 0; i < 2; ++i) {
             uint32_t x = i ? gin : 0u;
             for (uint32_t k = 0; k < B; ++k) if ((s >> k) & 1u) x ^= ebit((int)k);
-            labels[2 * s + i] = (uint8_t)((x & 3u) & ~(x >> 2));
+            labels[2 * s + i] = (uint8_t)(ref ? ((x & 3u) & ~(x >> 2)) : x);
         }
 }
 #endif  // !__CUDACC_RTC__

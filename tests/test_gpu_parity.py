@@ -282,6 +282,23 @@ def test_raw_iq_entry_matches_demapper_plus_decoder(cc, orc, torch_cuda):
         d.decode_iq_host(np.zeros((1, 42, 2), np.float32))
 
 
+@pytest.mark.parametrize("K,octal,L,F", [(9, ("557", "663", "711"), 1024, 21), (9, ("557", "663", "711"), 7, 133), (8, ("225", "331", "367"), 100, 70),
+                                          (10, ("1117", "1365", "1633"), 130, 19), (13, ("10533", "17661", "11271"), 40, 3)],
+                         ids=["k9-builtin-L1024", "k9-builtin-L7", "k8-nvrtc", "k10-nvrtc", "k13-nvrtc"])
+def test_rate_one_third_on_large_trellises(cc, orc, torch_cuda, K, octal, L, F):
+    """K >= 8, n = 3: the register-tile kernels with the 8-letter label alphabet (the reference decoder takes any
+    symlen_out at any K, AWGN-channel/viterbi-decoder.c:48-63), against the oracle and the table-driven kernels"""
+    code = cc.CodeParam(3, K, L, tuple(cc.codes.left_align(o, K) for o in octal))
+    oc = ocode(code, 1)
+    _, met = make_soft_inputs(orc, oc, F, 0.6, seed=K * 7 + L)
+    exp = orc.decode_soft(oc, met)
+    out, name = _decode_soft(cc, torch_cuda, code, 1, met)
+    assert name.startswith("tile_soft_f32<"), name
+    assert np.array_equal(out, exp), f"{name}: {(out != exp).any(axis=1).sum()} of {F} frames differ"
+    out2, name2 = _decode_soft(cc, torch_cuda, code, 1, met, flags=cc.FORCE_GENERIC)
+    assert name2.startswith("generic") and np.array_equal(out2, exp)
+
+
 def test_rate_one_codes(cc, orc, torch_cuda):
     """symlen_out = 1 (one coded bit per step, a 2-point constellation): accepted by vdec_create, served by the
     table-driven kernels; soft, hard and raw-I/Q entries against the oracle"""
@@ -417,11 +434,15 @@ PUBLISHED_BSC = {   # results/binary_symmetric_channel.m:5-13, 17 channel error 
 
 
 @pytest.mark.parametrize("idx", [0, 1, 2, 3, 5])
-def test_bsc_ber_table_agrees_with_published_results(cc, torch_cuda, idx):
+def test_bsc_ber_table_agrees_with_published_results(cc, orc, torch_cuda, idx):
     """the BSC driver's whole table (binary-symmetric-channel/main.c:103-109,147-176: 17 channel error rates) on the
     GPU — source, bit flips, hard-decision decoder, error count — against results/binary_symmetric_channel.m:5-13.
-    The published values are printed with six decimals: compared inside our 95 % interval widened by the published
-    run's spread and by half a unit of the last printed digit."""
+    The recorded table is 2 - 3 % BELOW what the reference's own code produces today at several points (code 1 at
+    p = 1.25 %: table 0.002472; unmodified pipeline with rand(), 8e7 bits: 0.002540; this GPU link: 0.002546; DESIGN.md
+    section 2), so the table is compared with a 6 % allowance on top of both runs' statistical spread and of half a unit
+    of its last printed digit — and two points per code are compared tightly with the UNMODIFIED compiled pipeline
+    (oracle/_ref/libref_bsc.so, libc rand()) where it travelled to this box."""
+    import oracle
     code = cc.get_code(idx)
     dec = cc.BatchDecoder(code, cc.HARD_U16, cc.PARITY_REF)
     rates = list(cc.BSC_RATES_PPM)
@@ -431,10 +452,24 @@ def test_bsc_ber_table_agrees_with_published_results(cc, torch_cuda, idx):
     for p, pub, r in zip(pts, PUBLISHED_BSC[idx], rates):
         pub_bits = 8e8 if r <= 12500 else 8e7 if r <= 50000 else 8e6 if r <= 200000 else 8e5
         lo, hi = _published_band(p, max(pub, 1e-9), pub_bits) if p["frame_errors"] else (0.0, p["ci95_hi"])
-        assert lo - 0.6e-6 <= pub <= hi + 0.6e-6, (idx, r, p, pub)
+        # errored frames of the catastrophic codes carry long bursts of very different lengths: 1.5 x the frame-count spread
+        ber = p["ber"]
+        lo, hi = ber - 1.5 * (ber - lo), ber + 1.5 * (hi - ber)
+        assert 0.94 * lo - 0.6e-6 <= pub <= 1.06 * hi + 0.6e-6, (idx, r, p, pub)
         if pub >= 1e-4:
             assert p["frame_errors"] >= 50, (idx, r, p)
     assert dec.kernel_name.startswith("regs2_hard_u16x2"), dec.kernel_name
+    if oracle.reference_available():
+        ref = oracle.Reference()
+        oc = ocode(code)
+        for r in (12500, 50000):
+            F = 100_000
+            payload, _, out, _ = ref.bsc_run(oc, F, 4242 + r, r)                       # encoder, rand() flips, decoder: all reference code
+            errs = np.unpackbits(out[:, :code.payload_bytes] ^ payload, axis=1)[:, :code.L]
+            ref_ber, ref_fe = errs.sum() / (F * code.L), int(errs.any(axis=1).sum())
+            p = pts[rates.index(r)]
+            rel = 1.5 * 1.96 * (1.0 / max(ref_fe, 1) + 1.0 / max(p["frame_errors"], 1)) ** 0.5
+            assert abs(p["ber"] - ref_ber) <= rel * ref_ber + 1e-7, (idx, r, p["ber"], ref_ber, ref_fe)
     dec.close()
 
 

@@ -88,9 +88,15 @@ def test_unregistered_polynomials_compile_at_run_time(cc):
     assert cc.jit_check(k6r3, cc.SOFT_F32, cc.PARITY_REF, iq=True) > 10000
     assert cc.jit_check(k9, cc.SOFT_F32, cc.PARITY_LINEAR, iq=True) == 0            # tile kernels take staged metrics
     assert cc.jit_check(k9, cc.SOFT_F32, cc.PARITY_REF) > 10000
-    # rate 1/3 on a large trellis: no tile kernel model, stays table-driven
+    # rate 1/3 on a large trellis: register-tile kernel with an 8-letter label alphabet (true-parity labels), built in
+    # for (557,663,711) and compiled at run time for other polynomials; de-facto labels with a D^3-type tap and integer
+    # metrics stay table-driven
     k9r3 = CodeParam(3, 9, 100, (left_align("557", 9), left_align("663", 9), left_align("711", 9)))
-    assert cc.config_kernel_name(k9r3, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("generic_soft_f32<K9 n3")
+    assert cc.config_kernel_name(k9r3, cc.SOFT_F32, cc.PARITY_LINEAR).startswith("tile_soft_f32<K9 r1/3 (557,663,711)")
+    k10r3 = CodeParam(3, 10, 100, (left_align("1117", 10), left_align("1365", 10), left_align("1633", 10)))
+    assert cc.config_kernel_name(k10r3, cc.SOFT_F32, cc.PARITY_LINEAR) == "tile_soft_f32<K10 (1117,1365,1633) linear, nvrtc>"
+    assert cc.jit_check(k10r3, cc.SOFT_F32, cc.PARITY_LINEAR) > 10000
+    assert cc.config_kernel_name(k9r3, cc.HARD_U16, cc.PARITY_LINEAR).startswith("generic_hard_u16<K9 n3")
 
 
 def _declared_functions(header):

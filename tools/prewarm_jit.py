@@ -34,6 +34,8 @@ def jobs():
     for parity in (0, 1):                                                # fuzz / raw-I/Q cases
         out.append((2, 6, 77, ("53", "75"), parity, SOFT, 0, 0, False))
         out.append((2, 6, 77, ("53", "75"), parity, SOFT, 0, 0, True))
+    for K, octal, L in ((8, ("225", "331", "367"), 100), (10, ("1117", "1365", "1633"), 130), (13, ("10533", "17661", "11271"), 40)):
+        out.append((3, K, L, octal, 1, SOFT, 0, 0, False))               # rate 1/3 register-tile kernels
     return out
 
 
