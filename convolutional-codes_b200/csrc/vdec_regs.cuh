@@ -42,6 +42,9 @@
 #ifndef VDEC_SIGN_LIN
 #define VDEC_SIGN_LIN 0
 #endif
+#ifndef VDEC_OPERAND_V4
+#define VDEC_OPERAND_V4 1
+#endif
 
 namespace vd {
 
@@ -416,6 +419,7 @@ struct SoftRing {
 
     uint32_t base;        // shared-window address of this lane's first piece
     uint32_t T;
+    float one, negzero;   // 1.0f and -0.0f as run-time values (get_pairs)
     const float* nextp;   // first step of the next group to prefetch (this lane's frame row)
     uint32_t next_t;      // its step index
     uint32_t woff;        // ring byte offset where that group goes
@@ -450,6 +454,8 @@ struct SoftRing {
     __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
         base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * PB;
         T = steps; nextp = row; next_t = 0; woff = 0; roff = 0;
+        one = __uint_as_float(0x3f800000u | (steps >> 31));          // steps < 2^31: exactly 1.0f and -0.0f
+        negzero = __uint_as_float(0x80000000u | (steps >> 31));
         prefetch_next();
         prefetch_next();
     }
@@ -465,9 +471,38 @@ struct SoftRing {
     // packed mode: fetch every operand pair (bm[x], bm[y]) that MASK names straight into a 64-bit
     // register pair with two scalar loads.  Volatile so that ptxas neither fuses them into a v4 load
     // (which pins four consecutive registers and costs two MOVs per FADD2 operand) nor drops them.
+    // VDEC_OPERAND_V4 (default): the step's M metrics come in with one LDS.128 per four (a lane's piece is 16 contiguous
+    // bytes: conflict-free, one wavefront per quarter warp) and the operand pairs are formed by register moves on the
+    // FMA pipes, which have slack.  The scalar form (two LDS.32 per pair, 4-way bank-conflicted by the 16-byte piece
+    // layout: 565 M of 761 M shared wavefronts were replays, profiles/r01y) stays selectable for A/B builds.
     template <uint64_t MASK, int PH>
     __device__ __forceinline__ void get_pairs(uint64_t (&bp)[M * M]) const {
         const uint32_t a = base + roff;
+        if constexpr (VDEC_OPERAND_V4 && PB == 16) {
+            float bm[M];
+            static_for<0, M / 4>([&](auto qc) {
+                constexpr int Q = decltype(qc)::value;
+                asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                             : "=f"(bm[4 * Q]), "=f"(bm[4 * Q + 1]), "=f"(bm[4 * Q + 2]), "=f"(bm[4 * Q + 3])
+                             : "r"(a), "n"(elem_off<PH>(4 * Q)));
+            });
+            // Each half of an operand pair is a COPY of a metric made by an exact identity on the FMA pipes,
+            // x * 1.0 + (-0.0) = x for every x (one, negzero: run-time values the compiler cannot fold), written
+            // straight into the aligned register pair FADD2 wants.  Plain moves out of the LDS.128 quad are
+            // copy-propagated by ptxas into two IMAD.MOV in front of almost every FADD2 (+ 70 % instructions).
+            static_for<0, M * M>([&](auto ic) {
+                constexpr int I = decltype(ic)::value, x = I / M, y = I % M;
+                if constexpr ((MASK >> I) & 1ull) {
+                    float lo, hi;
+                    asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(lo) : "f"(bm[x]), "f"(one), "f"(negzero));
+                    asm("fma.rn.f32 %0, %1, %2, %3;" : "=f"(hi) : "f"(bm[y]), "f"(one), "f"(negzero));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(bp[I]) : "f"(lo), "f"(hi));
+                } else {
+                    bp[I] = 0;
+                }
+            });
+            return;
+        }
         static_for<0, M * M>([&](auto ic) {
             constexpr int I = decltype(ic)::value, x = I / M, y = I % M;
             if constexpr ((MASK >> I) & 1ull) {

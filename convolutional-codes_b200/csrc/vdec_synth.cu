@@ -62,50 +62,102 @@ __global__ void payload_kernel(uint64_t nframes, uint64_t first, uint64_t seed, 
     }
 }
 
-// Encoder output for step t of a frame (encoder.c:84-119: bits enter MSB-first, steps >= L are the zero tail):
-// label of (state before step t, input bit t), state bit K-2 = previous input (viterbi-decoder.c:65-66).
-// The K input bits t-K+1 .. t are cut out of three payload bytes; bits outside [0, L) read as zero.
-__device__ __forceinline__ uint32_t enc_symbol(const uint8_t* __restrict__ pl, uint32_t t, uint32_t K, uint32_t L, uint32_t pb,
-                                               const uint8_t* __restrict__ labels) {
+// AWGN link: payload -> encoder -> mapper -> noise [-> demapper].
+//   * T even (every BASELINE shape): one thread makes kSynthPairs PAIRS of consecutive steps (t, t+1) of one frame.  One
+//     Philox4x32-10 call (4 words) feeds both symbols, the K+1 input bits of the pair are cut out of three payload
+//     bytes once, and I/Q leaves as one 16-byte store per pair.  Box-Muller on the SFU: lg2.approx, sqrt.approx,
+//     sin/cos.approx (absolute error ~1e-6 of sigma: irrelevant for a noise source, there is no parity target for it).
+//   * T odd: one thread per symbol, same random numbers (word pair 2*(t & 1) of Philox block (frame, t >> 1)).
+constexpr int kSynthPairs = 4, kSynthThreads = 256;
+
+// symbol of the step whose input bit sits at position 0 of `win` (older bits above it)
+__device__ __forceinline__ uint32_t label_of(uint32_t win, uint32_t K, const uint8_t* __restrict__ labels) {
+    const uint32_t state = __brev((win >> 1) & ((1u << (K - 1)) - 1u)) >> (33u - K);     // bit t-1 -> position K-2
+    return __ldg(labels + 2 * state + (win & 1u));
+}
+// input bits of a frame up to bit t (t at position 0, t-i at position i; bits outside [0, L) read as zero)
+__device__ __forceinline__ uint32_t input_window(const uint8_t* __restrict__ pl, uint32_t t, uint32_t L, uint32_t pb) {
     const int j = (int)(t >> 3);                                  // byte holding bit t
     uint32_t w = 0;                                               // bits 8(j-2) .. 8j+7, bit 8(j-2) at position 23
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         const int jj = j - 2 + b;
-        const uint32_t v = (jj >= 0 && jj < (int)pb) ? (uint32_t)__ldg(pl + jj) : 0u;
+        uint32_t v = 0;
+        if (jj >= 0 && jj < (int)pb) v = (uint32_t)__ldg(pl + jj);
         w = (w << 8) | v;
     }
-    const int base = 8 * (j - 2);
-    const int keep = (int)L - base;                               // bits of w that belong to the payload
+    const int keep = (int)L - 8 * (j - 2);                        // bits of w that belong to the payload
     if (keep < 24) w = keep <= 0 ? 0u : (w & ~((1u << (24 - keep)) - 1u));
-    const uint32_t win = w >> (7u - (t & 7u));                    // bit t at position 0, bit t-i at position i
-    const uint32_t in = win & 1u;
-    const uint32_t state = __brev((win >> 1) & ((1u << (K - 1)) - 1u)) >> (33u - K);     // bit t-1 -> position K-2
-    return labels[2 * state + in];
+    return w >> (7u - (t & 7u));
+}
+// Encoder output for step t (encoder.c:84-119: bits enter MSB-first, steps >= L are the zero tail): label of (state
+// before step t, input bit t), state bit K-2 = previous input (viterbi-decoder.c:65-66)
+__device__ __forceinline__ uint32_t enc_symbol(const uint8_t* __restrict__ pl, uint32_t t, uint32_t K, uint32_t L, uint32_t pb,
+                                               const uint8_t* __restrict__ labels) {
+    return label_of(input_window(pl, t, L, pb), K, labels);
 }
 
-// AWGN link for a run of symbols: payload -> encoder -> mapper -> noise [-> demapper].  One thread makes kPairs
-// PAIRS of consecutive symbols of the batch's [frame][step] sequence (one Philox call feeds one pair when both lie in
-// one frame at an even step, as all pairs do when T is even), so I/Q leaves as one 16-byte store per pair.
-constexpr int kSynthPairs = 4, kSynthThreads = 256;
-
-template <int N>
-__device__ __forceinline__ void synth_symbol(const LaunchGeom& g, const uint8_t* __restrict__ labels, const uint8_t* __restrict__ payload,
-                                             const float* s_c, uint32_t f, uint32_t t, uint32_t w0, uint32_t w1, float sigma,
-                                             float& x, float& y) {
-    const uint32_t pb = (g.L + 7) / 8;
-    const uint32_t sym = enc_symbol(payload + (size_t)f * pb, t, g.K, g.L, pb, labels);
-    // Box-Muller, one pair per symbol (I, Q)   (gaussian.c:18-38 uses the same transform on rand()); u1 in (0, 1]
-    // keeps the full 32 random bits where they matter (small u1 = large noise: tail to 6.7 sigma)
+// constellation point `sym` plus Gaussian noise of standard deviation sigma per dimension from two random words
+__device__ __forceinline__ void noisy_point(const float* s_c, uint32_t sym, uint32_t w0, uint32_t w1, float sigma, float& x, float& y) {
+    // Box-Muller, one pair per symbol (gaussian.c:18-38 uses the same transform on rand()); u1 in (0, 1] keeps all 32
+    // random bits where they matter (small u1 = large noise: the tail reaches 6.7 sigma)
     const float u1 = __fmaf_rn(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float ang = __fmaf_rn(__uint2float_rn(w1 >> 8), 3.7450702e-7f, -3.14159265f);      // [-pi, pi)
-    const float rad = sqrtf(fmaxf(-2.0f * __logf(u1), 0.0f));
-    float sn, cs;
-    __sincosf(ang, &sn, &cs);
-    x = __fadd_rn(s_c[2 * sym], __fmul_rn(sigma, rad * cs));                                 // main.c:100-102
-    y = __fadd_rn(s_c[2 * sym + 1], __fmul_rn(sigma, rad * sn));
+    float r2 = fmaxf(-2.0f * __logf(u1), 0.0f), rad;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(rad) : "f"(r2));
+    const float sr = sigma * rad;
+    x = __fmaf_rn(sr, __cosf(ang), s_c[2 * sym]);                                             // main.c:100-102
+    y = __fmaf_rn(sr, __sinf(ang), s_c[2 * sym + 1]);
 }
 
+template <int N>
+__device__ __forceinline__ void store_metrics(float* __restrict__ dst, float x, float y) {
+    constexpr int M = 1 << N;
+    float bm[M];
+    demap_point<N>(x, y, bm);
+    if constexpr (M == 2) *reinterpret_cast<float2*>(dst) = make_float2(bm[0], bm[1]);
+    else {
+#pragma unroll
+        for (int q = 0; q < M / 4; ++q)
+            reinterpret_cast<float4*>(dst)[q] = make_float4(bm[4 * q], bm[4 * q + 1], bm[4 * q + 2], bm[4 * q + 3]);
+    }
+}
+
+// T even.  npairs = nframes * T / 2 of this launch (< 2^31)
+template <int N, bool MET, bool IQ>
+__global__ void __launch_bounds__(kSynthThreads)
+synth_awgn_pairs_kernel(LaunchGeom g, const uint8_t* __restrict__ labels, uint32_t npairs, uint64_t first, uint64_t seed, float sigma,
+                        const uint8_t* __restrict__ payload, float* __restrict__ metrics, float* __restrict__ iq) {
+    constexpr int M = 1 << N;
+    __shared__ float s_c[2 * M];
+    if (threadIdx.x < 2 * M) s_c[threadIdx.x] = constellation(N)[threadIdx.x];
+    __syncthreads();
+    const uint32_t half = g.T >> 1, pb = (g.L + 7) / 8, K = g.K, L = g.L;
+    uint32_t p = blockIdx.x * (uint32_t)(kSynthThreads * kSynthPairs) + threadIdx.x;
+    if (p >= npairs) return;
+    uint32_t f = p / half, tp = p - f * half;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll 1
+    for (int r = 0; r < kSynthPairs && p < npairs; ++r) {
+        const uint64_t F = first + f;
+        uint32_t o[4];
+        philox4x32_10(k0, k1, (uint32_t)F, (uint32_t)(F >> 32), tp, 0x4E4F4953u, o);
+        const uint32_t t = 2 * tp;
+        const uint32_t win = input_window(payload + (size_t)f * pb, t + 1, L, pb);           // bit t+1 at position 0
+        float x0, y0, x1, y1;
+        noisy_point(s_c, label_of(win >> 1, K, labels), o[0], o[1], sigma, x0, y0);
+        noisy_point(s_c, label_of(win, K, labels), o[2], o[3], sigma, x1, y1);
+        if constexpr (IQ) reinterpret_cast<float4*>(iq)[p] = make_float4(x0, y0, x1, y1);
+        if constexpr (MET) {
+            store_metrics<N>(metrics + (size_t)p * (2 * M), x0, y0);
+            store_metrics<N>(metrics + (size_t)p * (2 * M) + M, x1, y1);
+        }
+        p += kSynthThreads; tp += kSynthThreads;
+        while (tp >= half) { tp -= half; ++f; }
+    }
+}
+
+// any T: one thread per symbol
 template <int N, bool MET, bool IQ>
 __global__ void __launch_bounds__(kSynthThreads)
 synth_awgn_kernel(LaunchGeom g, const uint8_t* __restrict__ labels, uint32_t nsym, uint64_t first, uint64_t seed, float sigma,
@@ -114,53 +166,16 @@ synth_awgn_kernel(LaunchGeom g, const uint8_t* __restrict__ labels, uint32_t nsy
     __shared__ float s_c[2 * M];
     if (threadIdx.x < 2 * M) s_c[threadIdx.x] = constellation(N)[threadIdx.x];
     __syncthreads();
-    const uint32_t T = g.T;
-    uint32_t s0 = 2u * (blockIdx.x * (uint32_t)(kSynthThreads * kSynthPairs) + threadIdx.x);       // first symbol of the pair
+    const uint32_t s0 = blockIdx.x * (uint32_t)kSynthThreads + threadIdx.x;
     if (s0 >= nsym) return;
-    uint32_t f = s0 / T, t = s0 - f * T;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll 1
-    for (int r = 0; r < kSynthPairs; ++r) {
-        if (s0 >= nsym) break;
-        float x[2], y[2];
-        const bool two = s0 + 1 < nsym;
-        uint32_t o[4];
-        const uint64_t F = first + f;
-        philox4x32_10(k0, k1, (uint32_t)F, (uint32_t)(F >> 32), t >> 1, 0x4E4F4953u, o);
-        if (!(t & 1u) && t + 1 < T) {                             // the common case: one Philox call, both symbols
-            synth_symbol<N>(g, labels, payload, s_c, f, t, o[0], o[1], sigma, x[0], y[0]);
-            if (two) synth_symbol<N>(g, labels, payload, s_c, f, t + 1, o[2], o[3], sigma, x[1], y[1]);
-        } else {                                                  // odd T: the pair straddles two Philox blocks or two frames
-            synth_symbol<N>(g, labels, payload, s_c, f, t, o[2 * (t & 1u)], o[2 * (t & 1u) + 1], sigma, x[0], y[0]);
-            if (two) {
-                const uint32_t f1 = t + 1 < T ? f : f + 1, t1 = t + 1 < T ? t + 1 : 0;
-                const uint64_t F1 = first + f1;
-                philox4x32_10(k0, k1, (uint32_t)F1, (uint32_t)(F1 >> 32), t1 >> 1, 0x4E4F4953u, o);
-                synth_symbol<N>(g, labels, payload, s_c, f1, t1, o[2 * (t1 & 1u)], o[2 * (t1 & 1u) + 1], sigma, x[1], y[1]);
-            }
-        }
-        if constexpr (IQ) {
-            if (two) *reinterpret_cast<float4*>(iq + 2 * (size_t)s0) = make_float4(x[0], y[0], x[1], y[1]);
-            else *reinterpret_cast<float2*>(iq + 2 * (size_t)s0) = make_float2(x[0], y[0]);
-        }
-        if constexpr (MET) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if (e == 1 && !two) break;
-                float bm[M];
-                demap_point<N>(x[e], y[e], bm);
-                float* dst = metrics + (size_t)(s0 + e) * M;
-                if constexpr (M == 2) *reinterpret_cast<float2*>(dst) = make_float2(bm[0], bm[1]);
-                else {
-#pragma unroll
-                    for (int q = 0; q < M / 4; ++q)
-                        reinterpret_cast<float4*>(dst)[q] = make_float4(bm[4 * q], bm[4 * q + 1], bm[4 * q + 2], bm[4 * q + 3]);
-                }
-            }
-        }
-        s0 += 2u * kSynthThreads; t += 2u * kSynthThreads;
-        while (t >= T) { t -= T; ++f; }
-    }
+    const uint32_t f = s0 / g.T, t = s0 - f * g.T, pb = (g.L + 7) / 8;
+    const uint64_t F = first + f;
+    uint32_t o[4];
+    philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)F, (uint32_t)(F >> 32), t >> 1, 0x4E4F4953u, o);
+    float x, y;
+    noisy_point(s_c, enc_symbol(payload + (size_t)f * pb, t, g.K, g.L, pb, labels), (t & 1u) ? o[2] : o[0], (t & 1u) ? o[3] : o[1], sigma, x, y);
+    if constexpr (IQ) reinterpret_cast<float2*>(iq)[s0] = make_float2(x, y);
+    if constexpr (MET) store_metrics<N>(metrics + (size_t)s0 * M, x, y);
 }
 
 __global__ void synth_bsc_kernel(LaunchGeom g, const uint8_t* __restrict__ labels, uint64_t nframes, uint64_t first,
@@ -209,31 +224,45 @@ __global__ void hard_demap_kernel(uint32_t n, const float* __restrict__ iq, uint
     for (uint32_t k = 0; k < M; ++k) metrics[i * M + k] = demap_one(c, k, sx, sy, nd);
 }
 
-// one thread per frame: compare the first L decoded bits with the payload (main.c:129-141)
-__global__ void count_errors_kernel(const uint8_t* __restrict__ dec, const uint8_t* __restrict__ payload, uint64_t nframes,
-                                    uint32_t L, uint32_t out_bytes, unsigned long long* __restrict__ counters) {
-    const uint64_t f = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    uint32_t errs = 0;
-    if (f < nframes) {
-        const uint32_t pb = (L + 7) / 8;
+// Compare the first L decoded bits of every frame with its payload (main.c:129-141).  One warp per frame at a time
+// (lanes read consecutive bytes of the two rows: coalesced although the decoded rows are (T+7)/8 bytes apart and hence
+// unaligned), kCountFrames frames per warp, one pair of atomics per CTA.
+constexpr int kCountThreads = 256, kCountFrames = 8;
+
+__global__ void __launch_bounds__(kCountThreads)
+count_errors_kernel(const uint8_t* __restrict__ dec, const uint8_t* __restrict__ payload, uint64_t nframes,
+                    uint32_t L, uint32_t out_bytes, unsigned long long* __restrict__ counters) {
+    __shared__ uint32_t s_err[kCountThreads / 32], s_ferr[kCountThreads / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t pb = (L + 7) / 8;
+    const uint32_t last_mask = (L & 7) ? ((0xFF00u >> (L & 7)) & 0xFFu) : 0xFFu;      // only the first L bits count
+    const uint64_t f0 = ((uint64_t)blockIdx.x * (kCountThreads / 32) + warp) * kCountFrames;
+    uint32_t errs = 0, ferr = 0;
+    for (int k = 0; k < kCountFrames; ++k) {
+        const uint64_t f = f0 + k;
+        if (f >= nframes) break;
         const uint8_t* d = dec + f * out_bytes; const uint8_t* p = payload + f * pb;
-        for (uint32_t j = 0; j < pb; ++j) {
-            uint32_t x = (uint32_t)(d[j] ^ p[j]);
-            if (j == pb - 1 && (L & 7)) x &= (0xFF00u >> (L & 7)) & 0xFFu;      // only the first L bits count
-            errs += __popc(x);
+        uint32_t e = 0;
+        for (uint32_t j = lane; j < pb; j += 32) {
+            uint32_t x = (uint32_t)(__ldg(d + j) ^ __ldg(p + j));
+            if (j == pb - 1) x &= last_mask;
+            e += __popc(x);
         }
+        e = __reduce_add_sync(0xffffffffu, e);
+        errs += e; ferr += e ? 1u : 0u;
     }
-    uint32_t ferr = errs ? 1u : 0u;
+    if (lane == 0) { s_err[warp] = errs; s_ferr[warp] = ferr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0, b = 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        errs += __shfl_down_sync(0xffffffffu, errs, off);
-        ferr += __shfl_down_sync(0xffffffffu, ferr, off);
+        for (int w = 0; w < kCountThreads / 32; ++w) { a += s_err[w]; b += s_ferr[w]; }
+        if (a | b) {
+            atomicAdd(counters + 1, (unsigned long long)a);
+            atomicAdd(counters + 2, (unsigned long long)b);
+        }
+        if (blockIdx.x == 0) atomicAdd(counters, (unsigned long long)nframes * L);
     }
-    if ((threadIdx.x & 31) == 0 && (errs | ferr)) {
-        atomicAdd(counters + 1, (unsigned long long)errs);
-        atomicAdd(counters + 2, (unsigned long long)ferr);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counters, (unsigned long long)nframes * L);
 }
 
 // sliding-window stitching: block b contributes bytes [skip, skip + keep) of its output row (the last block
@@ -255,7 +284,7 @@ inline unsigned grid_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 
 int count_errors_launch(const uint8_t* dec, const uint8_t* payload, uint64_t nframes, uint32_t L, uint32_t out_bytes,
                         uint64_t* counters, cudaStream_t st) {
     if (nframes == 0) return 0;
-    count_errors_kernel<<<grid_for(nframes, 256), 256, 0, st>>>(dec, payload, nframes, L, out_bytes,
+    count_errors_kernel<<<grid_for(nframes, (kCountThreads / 32) * kCountFrames), kCountThreads, 0, st>>>(dec, payload, nframes, L, out_bytes,
                                                                 reinterpret_cast<unsigned long long*>(counters));
     VDEC_CUDA(cudaGetLastError());
     return 0;
@@ -282,10 +311,18 @@ int demap_launch(uint32_t n, const float* iq, uint64_t nsym, float* metrics, cud
 template <int N>
 static int synth_awgn_n(const LaunchGeom& g, const uint8_t* labels_dev, uint32_t nsym, uint64_t first, uint64_t seed, float sigma,
                         const uint8_t* payload, float* metrics, float* iq, cudaStream_t st) {
-    const unsigned grid = grid_for(((uint64_t)nsym + 1) / 2, kSynthThreads * kSynthPairs);
-    if (metrics && iq) synth_awgn_kernel<N, true, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
-    else if (metrics) synth_awgn_kernel<N, true, false><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
-    else synth_awgn_kernel<N, false, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
+    if ((g.T & 1u) == 0) {
+        const uint32_t npairs = nsym / 2;
+        const unsigned grid = grid_for(npairs, kSynthThreads * kSynthPairs);
+        if (metrics && iq) synth_awgn_pairs_kernel<N, true, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, npairs, first, seed, sigma, payload, metrics, iq);
+        else if (metrics) synth_awgn_pairs_kernel<N, true, false><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, npairs, first, seed, sigma, payload, metrics, iq);
+        else synth_awgn_pairs_kernel<N, false, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, npairs, first, seed, sigma, payload, metrics, iq);
+    } else {
+        const unsigned grid = grid_for(nsym, kSynthThreads);
+        if (metrics && iq) synth_awgn_kernel<N, true, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
+        else if (metrics) synth_awgn_kernel<N, true, false><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
+        else synth_awgn_kernel<N, false, true><<<grid, kSynthThreads, 0, st>>>(g, labels_dev, nsym, first, seed, sigma, payload, metrics, iq);
+    }
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -299,9 +336,8 @@ int synth_awgn_launch(const LaunchGeom& g, const uint8_t* labels_dev, uint64_t n
     const uint32_t pb = (g.L + 7) / 8;
     payload_kernel<<<grid_for(nframes * ((pb + 3) / 4), 256), 256, 0, st>>>(nframes, first, seed, pb, payload);
     VDEC_CUDA(cudaGetLastError());
-    // symbol indices are 32-bit inside a launch; launches start on even frame counts so that pairs stay aligned
-    uint64_t chunk = (0xF0000000ull / g.T) & ~1ull;    // head room: the kernel steps its 32-bit symbol index past the end
-    if (chunk < 2) chunk = 2;
+    uint64_t chunk = 0xF0000000ull / g.T;          // symbol indices are 32-bit inside a launch
+    if (chunk < 1) chunk = 1;
     for (uint64_t done = 0; done < nframes; done += chunk) {
         const uint64_t nf = nframes - done < chunk ? nframes - done : chunk;
         const uint32_t nsym = (uint32_t)(nf * g.T);
