@@ -155,6 +155,8 @@ def run_reference(args) -> int:
 # --------------------------------------------------------------------------------------------------
 def set_cpu_affinity(local: int) -> str:
     """Bind this rank to the CPUs next to its GPU before pinned host memory is first touched (NUMA-local staging)."""
+    if os.environ.get("BENCH_NO_AFFINITY"):
+        return "disabled (BENCH_NO_AFFINITY)"
     try:
         import pynvml
         import torch
@@ -205,6 +207,7 @@ def run_configs(cc, torch, local: int, alu_peak_ops: float, hbm_peak_gbs: float,
         ("C2-quant", "K=7 (171,133) quantised soft (u8 metrics <= 7), packed 16-bit", C.K7_R12, "quant", cc.PARITY_REF, 1000000 // q, 0),
         ("C3", "K=7 rate-1/3 (133,171,165) soft, 8-point constellation, L=1024, reference labels", C.K7_R13, "soft", cc.PARITY_REF, 500000 // q, 0),
         ("C3-textbook", "K=7 rate-1/3 soft, true-parity labels", C.K7_R13, "soft", cc.PARITY_LINEAR, 500000 // q, 0),
+        ("C3-iq", "K=7 rate-1/3 from raw I/Q: the simulation's soft demapper (common/demapper.c) inside the decoder kernel's feeder", C.K7_R13, "iq", cc.PARITY_REF, 500000 // q, 0),
         ("C4-K9", "K=9 (561,753) soft, L=1024, survivors in HBM, true-parity labels", C.K9_R12, "soft", cc.PARITY_LINEAR, 131072 // q, 0),
         ("C4-K9-ref", "K=9 (561,753) soft, reference labels", C.K9_R12, "soft", cc.PARITY_REF, 131072 // q, 0),
         ("C4-K15", "K=15 (46321,51271) soft, 16384 states, L=1024, survivors in HBM, true-parity labels", C.K15_R12, "soft", cc.PARITY_LINEAR, 2368 // min(q, 2), 0),
@@ -300,9 +303,16 @@ def run_gpu(args) -> int:
     # One step of the sharded simulation (AWGN-channel/main.c:108-141 for a whole batch): decode the rank's frames,
     # count bit / frame errors against the payload, and sum the three counters over the ranks — the path's ONE
     # collective (NCCL all-reduce of 24 bytes), inside the timed region.
-    def step():
+    kev = []                                              # (start, end) events around the decoder launch of every timed step
+
+    def step(timed=False):
         counters.zero_()
+        if timed:
+            kev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            kev[-1][0].record()
         dec.decode(metrics, out=out)                      # vdec_decode_device on torch's current stream
+        if timed:
+            kev[-1][1].record()
         dec.count_errors(out, payload, counters)
         cc.allreduce_counters(counters)
 
@@ -311,24 +321,18 @@ def run_gpu(args) -> int:
     barrier()
     l0 = dec.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dec_ms = 0.0
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(args.steps):
-            step()
+            step(timed=True)
         e1.record()
         barrier()
     ms_total = e0.elapsed_time(e1)
     launches = dec.launches - l0
-    # the decoder kernel alone, same buffers, same stream (CUDA events around the launches only): the roofline's kernel time
-    torch.cuda.synchronize()
-    d0.record()
-    for _ in range(args.steps):
-        dec.decode(metrics, out=out)
-    d1.record()
-    torch.cuda.synchronize()
-    dec_ms = d0.elapsed_time(d1) / args.steps
+    # the decoder kernel alone: CUDA events on the launching stream around its launch inside the very same timed steps
+    # (the SM clock of this part steps down from 1965 MHz within ~60 ms of sustained load, so a separate loop would not
+    # measure the same kernel time)
+    dec_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
