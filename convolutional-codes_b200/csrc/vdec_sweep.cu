@@ -76,11 +76,14 @@ struct Dev {
     uint64_t* counters = nullptr;  // [3], this batch
 };
 
+// communicators are created once per device list and kept for the life of the process (ncclCommInitAll costs ~1 s)
+struct CommSet { std::vector<int> ids; std::vector<ncclComm_t> comm; };
+std::vector<CommSet> g_comms;
+
 struct Sweep {
     std::vector<Dev> dev;
-    std::vector<ncclComm_t> comm;
+    ncclComm_t* comm = nullptr;
     ~Sweep() {
-        for (ncclComm_t c : comm) if (c) g_nccl.CommDestroy(c);
         for (Dev& d : dev) {
             if (d.id < 0) continue;
             cudaSetDevice(d.id);
@@ -121,7 +124,8 @@ extern "C" int vdec_sweep(const struct vdec_config* cfg, const struct vdec_sweep
 
     Sweep s;
     s.dev.resize(ndev);
-    const uint32_t chunk = sw->chunk_frames ? sw->chunk_frames : 65536u;
+    // frames per launch and device: four full waves of the register kernels (148 SMs x 4 CTAs x 128 frames)
+    const uint32_t chunk = sw->chunk_frames ? sw->chunk_frames : 4u * 148u * 4u * 128u;
     for (int r = 0; r < ndev; ++r) {
         Dev& d = s.dev[r];
         vdec_config c = *cfg;
@@ -139,10 +143,14 @@ extern "C" int vdec_sweep(const struct vdec_config* cfg, const struct vdec_sweep
     }
     if (ndev > 1) {
         if (!load_nccl()) return -1;
-        s.comm.assign(ndev, nullptr);
         std::vector<int> ids(ndev);
         for (int r = 0; r < ndev; ++r) ids[r] = s.dev[r].id;
-        VDEC_NCCL(g_nccl.CommInitAll(s.comm.data(), ndev, ids.data()));
+        for (CommSet& c : g_comms) if (c.ids == ids) s.comm = c.comm.data();
+        if (!s.comm) {
+            g_comms.push_back(CommSet{ids, std::vector<ncclComm_t>(ndev, nullptr)});
+            VDEC_NCCL(g_nccl.CommInitAll(g_comms.back().comm.data(), ndev, ids.data()));
+            s.comm = g_comms.back().comm.data();
+        }
     }
 
     std::vector<uint64_t> done(npoints, 0);

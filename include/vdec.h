@@ -203,7 +203,7 @@ struct vdec_sweep_config {
     uint64_t frames_per_batch;    /* frames per point and batch, all devices together */
     uint64_t max_frames;          /* with min_frame_errors: give up on a point after this many frames (0 = no limit) */
     uint64_t min_frame_errors;    /* 0 = one batch per point */
-    uint32_t chunk_frames;        /* frames per launch and device, 0 = 65536 */
+    uint32_t chunk_frames;        /* frames per launch and device, 0 = 303104 (four full waves of the register kernels) */
     uint32_t channel;             /* enum vdec_channel */
     const char* resume_path;      /* optional: counters are appended here after every batch and picked up on restart */
 };
