@@ -43,6 +43,7 @@ EXPORTS = {
     "vdec_stream_decode_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
                                             C.c_void_p, C.c_void_p]),
     "vdec_sync": (C.c_int, [C.c_void_p]),
+    "vdec_debug_check": (C.c_long, [C.c_void_p]),
     "vdec_launch_count": (C.c_uint64, [C.c_void_p]),
     "vdec_count_errors_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "vdec_demap_device": (C.c_int, [C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

@@ -31,6 +31,12 @@ static size_t in_bytes_per_frame(const vdec* h) {
 // survivor scratch, one slot per concurrently running stream (0: decode_device, 1/2: host pipeline)
 struct vdec_scratch { uint32_t* p[3]; size_t bytes[3]; };
 
+// Guard zones (environment VDEC_GUARD=1 at vdec_create): every device buffer the library allocates for itself gets
+// kGuardBytes of a known pattern on either side, and vdec_debug_check() counts the guard bytes that changed — a
+// bounds check of the kernels' WRITES that needs no external tool (compute-sanitizer is not available on this pool).
+static const size_t kGuardBytes = 4096;
+static const unsigned char kGuardPattern = 0xA5;
+
 // kept out of the public struct to keep vdec_internal.h small
 struct vdec_priv {
     vdec base;
@@ -45,9 +51,38 @@ struct vdec_priv {
     size_t iq_frames;
     const vd::JitEntry* jit_iq;   // run-time compiled register kernel with the raw-I/Q feeder (compiled on first use)
     bool jit_iq_tried;
+    bool guard;                   // VDEC_GUARD: allocations carry guard zones
 };
 
+// cudaMalloc / cudaFree of the library's own buffers, with guard zones when asked for
+static cudaError_t guarded_malloc(vdec_priv* p, void** out, size_t bytes);
+static void guarded_free(vdec_priv* p, void* ptr);
+
 static vdec_priv* priv(vdec_t* h) { return reinterpret_cast<vdec_priv*>(h); }
+
+struct GuardRec { void* user; size_t bytes; };
+static GuardRec g_guards[64];
+static int g_nguards = 0;
+
+static cudaError_t guarded_malloc(vdec_priv* p, void** out, size_t bytes) {
+    if (!p->guard) return cudaMalloc(out, bytes);
+    unsigned char* base = nullptr;
+    const size_t padded = (bytes + 255) & ~(size_t)255;                // keep the tail guard aligned
+    cudaError_t e = cudaMalloc(&base, padded + 2 * kGuardBytes);
+    if (e != cudaSuccess) return e;
+    cudaMemset(base, kGuardPattern, kGuardBytes);
+    cudaMemset(base + kGuardBytes + bytes, kGuardPattern, padded - bytes + kGuardBytes);
+    *out = base + kGuardBytes;
+    if (g_nguards < 64) g_guards[g_nguards++] = GuardRec{*out, bytes};
+    return cudaSuccess;
+}
+static void guarded_free(vdec_priv* p, void* ptr) {
+    if (!ptr) return;
+    if (!p->guard) { cudaFree(ptr); return; }
+    for (int i = 0; i < g_nguards; ++i)
+        if (g_guards[i].user == ptr) { g_guards[i] = g_guards[--g_nguards]; break; }
+    cudaFree(static_cast<unsigned char*>(ptr) - kGuardBytes);
+}
 
 static int ensure_scratch(vdec_priv* p, int slot, const vd::LaunchGeom& geom, uint32_t frames) {
     vdec* h = &p->base;
@@ -56,8 +91,8 @@ static int ensure_scratch(vdec_priv* p, int slot, const vd::LaunchGeom& geom, ui
     const size_t need = h->jit ? vd::jit_bytes(h->jit, g) : h->tile2 ? vd::tile2_bytes(h->tile2, g) : h->tile ? vd::tile_bytes(h->tile, g) : h->regsw ? vd::regsw_bytes(h->regsw, g) : h->regs2 ? vd::regs2_bytes(h->regs2, g)
                         : h->regs ? h->regs->surv_bytes(g) : vd::generic_surv_bytes(g);
     if (need <= p->sc.bytes[slot]) return 0;
-    if (p->sc.p[slot]) { VDEC_CUDA(cudaFree(p->sc.p[slot])); p->sc.p[slot] = nullptr; p->sc.bytes[slot] = 0; }
-    VDEC_CUDA(cudaMalloc(&p->sc.p[slot], need));
+    if (p->sc.p[slot]) { guarded_free(p, p->sc.p[slot]); p->sc.p[slot] = nullptr; p->sc.bytes[slot] = 0; }
+    VDEC_CUDA(guarded_malloc(p, reinterpret_cast<void**>(&p->sc.p[slot]), need));
     p->sc.bytes[slot] = need;
     return 0;
 }
@@ -96,8 +131,8 @@ static int decode_iq_on(vdec_priv* p, int slot, const float* iq_dev, uint64_t nf
     if (chunk < 1) chunk = 1;
     if (chunk > nframes) chunk = nframes;
     if (chunk > p->met_frames[slot]) {
-        if (p->met[slot]) { VDEC_CUDA(cudaFree(p->met[slot])); p->met[slot] = nullptr; p->met_frames[slot] = 0; }
-        VDEC_CUDA(cudaMalloc(&p->met[slot], chunk * g.T * g.M * sizeof(float)));
+        if (p->met[slot]) { guarded_free(p, p->met[slot]); p->met[slot] = nullptr; p->met_frames[slot] = 0; }
+        VDEC_CUDA(guarded_malloc(p, reinterpret_cast<void**>(&p->met[slot]), chunk * g.T * g.M * sizeof(float)));
         p->met_frames[slot] = chunk;
     }
     for (uint64_t done = 0; done < nframes; done += chunk) {
@@ -262,6 +297,7 @@ int vdec_create(vdec_t** out, const struct vdec_config* cfg) {
     vdec* h = &p->base;
     h->cfg = *cfg;
     h->device = cfg->device;
+    { const char* g = getenv("VDEC_GUARD"); p->guard = g && *g && *g != '0'; }
     vd::LaunchGeom& g = h->geom;
     g.K = cfg->constr_len; g.n = cfg->symlen_out; g.L = cfg->block_len;
     g.S = 1u << (g.K - 1); g.T = g.L + g.K - 1; g.M = 1u << g.n;
@@ -334,9 +370,9 @@ void vdec_destroy(vdec_t* h) {
     if (!h) return;
     vdec_priv* p = priv(h);
     cudaSetDevice(h->device);
-    for (int i = 0; i < 3; ++i) if (p->sc.p[i]) cudaFree(p->sc.p[i]);
-    for (int i = 0; i < 3; ++i) if (p->met[i]) cudaFree(p->met[i]);
-    if (p->stream_tmp) cudaFree(p->stream_tmp);
+    for (int i = 0; i < 3; ++i) guarded_free(p, p->sc.p[i]);
+    for (int i = 0; i < 3; ++i) guarded_free(p, p->met[i]);
+    guarded_free(p, p->stream_tmp);
     for (int i = 0; i < 2; ++i) { if (p->iq_dev[i]) cudaFree(p->iq_dev[i]); if (p->iq_out[i]) cudaFree(p->iq_out[i]); }
     for (int i = 0; i < 2; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
@@ -537,8 +573,8 @@ static int stream_pass(vdec_priv* p, const uint8_t* in, size_t step_bytes, uint6
     g.stride_steps = stride; g.init_all_from = known_first ? 1u : 0u;
     const size_t need = nblk * g.out_bytes;
     if (need > p->stream_tmp_bytes) {
-        if (p->stream_tmp) { VDEC_CUDA(cudaFree(p->stream_tmp)); p->stream_tmp = nullptr; p->stream_tmp_bytes = 0; }
-        VDEC_CUDA(cudaMalloc(&p->stream_tmp, need));
+        if (p->stream_tmp) { guarded_free(p, p->stream_tmp); p->stream_tmp = nullptr; p->stream_tmp_bytes = 0; }
+        VDEC_CUDA(guarded_malloc(p, reinterpret_cast<void**>(&p->stream_tmp), need));
         p->stream_tmp_bytes = need;
     }
     if (decode_geom(p, 0, g, in + start_step * step_bytes, nblk, p->stream_tmp, nullptr, st) != 0) return -1;
@@ -578,6 +614,32 @@ int vdec_stream_decode_device(vdec_t* h, const void* in_dev, uint64_t nsteps, ui
     const uint64_t s0 = nfull * Lb - D, rest_bits = nsteps - nfull * Lb;
     return stream_pass(p, in, step_bytes, s0, 1, (uint32_t)(nsteps - s0), (uint32_t)(nsteps - s0), false, (uint32_t)D, 0,
                        (rest_bits + 7) / 8, out_dev + nfull * (Lb / 8), st);
+}
+
+long vdec_debug_check(vdec_t* h) {
+    if (!h) return -1;
+    vdec_priv* p = priv(h);
+    if (!p->guard) { vd::set_error("vdec_debug_check: the handle was not created with VDEC_GUARD=1"); return -1; }
+    VDEC_CUDA(cudaSetDevice(h->device));
+    VDEC_CUDA(cudaDeviceSynchronize());
+    long bad = 0;
+    unsigned char* host = static_cast<unsigned char*>(malloc(kGuardBytes + 256));
+    if (!host) return -1;
+    void* bufs[] = {p->sc.p[0], p->sc.p[1], p->sc.p[2], p->met[0], p->met[1], p->met[2], p->stream_tmp};
+    for (void* u : bufs) {
+        if (!u) continue;
+        size_t bytes = 0;
+        for (int i = 0; i < g_nguards; ++i) if (g_guards[i].user == u) bytes = g_guards[i].bytes;
+        const size_t padded = (bytes + 255) & ~(size_t)255;
+        unsigned char* base = static_cast<unsigned char*>(u) - kGuardBytes;
+        if (cudaMemcpy(host, base, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) { free(host); return -1; }
+        for (size_t i = 0; i < kGuardBytes; ++i) bad += host[i] != kGuardPattern;
+        const size_t tail = padded - bytes + kGuardBytes;
+        if (cudaMemcpy(host, base + kGuardBytes + bytes, tail, cudaMemcpyDeviceToHost) != cudaSuccess) { free(host); return -1; }
+        for (size_t i = 0; i < tail; ++i) bad += host[i] != kGuardPattern;
+    }
+    free(host);
+    return bad;
 }
 
 int vdec_sync(vdec_t* h) {

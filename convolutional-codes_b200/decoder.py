@@ -194,6 +194,13 @@ class BatchDecoder:
         if self.lib.vdec_sync(self.h) != 0:
             raise VdecError(_lib.last_error())
 
+    def debug_check(self) -> int:
+        """guard bytes around the library's own device buffers that were overwritten (handle created under VDEC_GUARD=1)"""
+        n = int(self.lib.vdec_debug_check(self.h))
+        if n < 0:
+            raise VdecError(_lib.last_error())
+        return n
+
     # -- the stages either side of the decoder ----------------------------------------------------
     def synth_awgn(self, nframes: int, first_frame: int, seed: int, sigma: float, want_iq: bool = False, stream=None,
                    want_metrics: bool = True):

@@ -146,6 +146,12 @@ enum vdec_stream_flags { VDEC_STREAM_START_KNOWN = 1u /* the stream begins in st
 int vdec_stream_decode_device(vdec_t* h, const void* in_dev, uint64_t nsteps, uint32_t block_steps, uint32_t depth,
                               uint32_t flags, uint8_t* out_dev, void* cuda_stream);
 int vdec_sync(vdec_t* h);
+/* Bounds check of the kernels' writes without external tools: a handle created with the environment variable
+ * VDEC_GUARD=1 puts 4 KiB guard zones around every buffer the library allocates for itself (survivor scratch, metric
+ * staging, sliding-window staging); this synchronises and returns the number of guard bytes that were overwritten
+ * (0 = clean, -1 = not a guarded handle).  Callers guard their own input / output buffers the same way
+ * (tests/test_gpu_parity.py::test_no_out_of_bounds_writes). */
+long vdec_debug_check(vdec_t* h);
 /* number of this library's kernels launched through `h` so far */
 uint64_t vdec_launch_count(const vdec_t* h);
 

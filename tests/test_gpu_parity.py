@@ -538,6 +538,66 @@ def test_stream_decode_falls_back_when_the_window_breaks_packed_limits(cc, orc, 
     qd.close(); sd.close()
 
 
+def test_no_out_of_bounds_writes(cc, torch_cuda, monkeypatch):
+    """compute-sanitizer is closed on this GPU pool, so the bounds check is the library's own: handles created under
+    VDEC_GUARD=1 wrap every internal device buffer (survivor scratch, staging) in guard zones, and the caller-side
+    buffers here sit inside canary-filled allocations.  Every kernel family, ragged frame counts and lengths."""
+    torch = torch_cuda
+    monkeypatch.setenv("VDEC_GUARD", "1")
+    C = cc.codes
+    G = 4096
+
+    def guarded(shape, dtype):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        raw = torch.full((n + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[G:G + n].view(dtype).view(*shape)
+
+    def intact(raw, n):
+        return bool((raw[:G] == 0xA5).all()) and bool((raw[G + n:] == 0xA5).all())
+
+    cases = [(C.K7_R12.with_block_len(1024), cc.SOFT_F32, 0, 0, 131), (C.K7_R12.with_block_len(77), cc.SOFT_F32, 1, 0, 33),
+             (C.K7_R13.with_block_len(250), cc.SOFT_F32, 0, 0, 65), (cc.get_code(0), cc.SOFT_F32, 0, 0, 1000),
+             (cc.get_code(5), cc.HARD_U16, 0, 0, 257), (C.K7_R12.with_block_len(300), cc.HARD_U16, 1, 0, 129),
+             (C.K7_R12.with_block_len(300), cc.HARD_U16, 1, cc.PREFER_32BIT, 129), (C.K7_R12.with_block_len(100), cc.SOFT_U8, 1, 0, 67),
+             (C.K8_R12.with_block_len(100), cc.SOFT_F32, 0, 0, 37), (C.K9_R12.with_block_len(131), cc.SOFT_F32, 1, 0, 19),
+             (C.K9_R12.with_block_len(131), cc.SOFT_F32, 1, cc.PREFER_LANEGROUP, 19), (C.K9_R12.with_block_len(64), cc.HARD_U16, 1, 0, 21),
+             (C.K12_R12.with_block_len(40), cc.SOFT_F32, 1, 0, 7), (C.K15_R12.with_block_len(20), cc.SOFT_F32, 1, 0, 3),
+             (cc.CodeParam(3, 9, 50, tuple(C.left_align(o, 9) for o in ("557", "663", "711"))), cc.SOFT_F32, 1, 0, 9),
+             (C.K7_R12.with_block_len(90), cc.SOFT_F32, 0, cc.FORCE_GENERIC, 11), (C.K9_R12.with_block_len(30), cc.HARD_U16, 0, cc.FORCE_GENERIC, 5),
+             (cc.CodeParam(2, 6, 77, (C.left_align("53", 6), C.left_align("75", 6))), cc.SOFT_F32, 1, 0, 45)]
+    for code, metric, parity, flags, F in cases:
+        dec = cc.BatchDecoder(code, metric, parity, flags=flags, metric_max=7 if metric == cc.SOFT_U8 else 0)
+        if metric == cc.SOFT_F32:
+            _, x0, iq0 = dec.synth_awgn(F, 0, 3, 0.5, want_iq=True)
+        elif metric == cc.SOFT_U8:
+            _, xf = dec.synth_awgn(F, 0, 3, 0.5)
+            x0 = torch.clamp(torch.round(xf * 2.0), max=7).to(torch.uint8)
+        else:
+            _, x0 = dec.synth_bsc(F, 0, 3, 40000)
+        rin, x = guarded(tuple(x0.shape), x0.dtype)
+        x.copy_(x0)
+        rout, out = guarded((F, dec.out_bytes), torch.uint8)
+        rpm, pm = guarded((F,), torch.int32)
+        dec.decode(x, out=out, path_metric=pm)
+        ref_out = dec.decode(x0)
+        ref_out = ref_out[0] if isinstance(ref_out, tuple) else ref_out
+        assert torch.equal(out, ref_out), dec.kernel_name
+        if metric == cc.SOFT_F32:
+            riq, iq = guarded(tuple(iq0.shape), torch.float32)
+            iq.copy_(iq0)
+            out.fill_(0)
+            dec.decode_iq(iq, out=out)
+            assert torch.equal(out, ref_out), dec.iq_kernel_name
+            assert intact(riq, iq0.numel() * 4), dec.iq_kernel_name
+            if code.K <= 9 and flags == 0:
+                st = dec.decode_stream(x.reshape(-1, code.M), 64, 32, start_known=True)
+                assert st.numel() == (F * code.T + 7) // 8
+        torch.cuda.synchronize()
+        assert intact(rin, x0.numel() * x0.element_size()) and intact(rout, F * dec.out_bytes) and intact(rpm, 4 * F), dec.kernel_name
+        assert dec.debug_check() == 0, dec.kernel_name
+        dec.close()
+
+
 def test_misaligned_soft_input_is_refused(cc, torch_cuda):
     torch = torch_cuda
     code = cc.codes.K7_R12.with_block_len(10)
