@@ -420,6 +420,7 @@ struct SoftRing {
     uint32_t base;        // shared-window address of this lane's first piece
     uint32_t T;
     float one, negzero;   // 1.0f and -0.0f as run-time values (get_pairs)
+    const unsigned char* gbase;   // generic address of this lane's first piece (VDEC_OPERAND_V4 == 2)
     const float* nextp;   // first step of the next group to prefetch (this lane's frame row)
     uint32_t next_t;      // its step index
     uint32_t woff;        // ring byte offset where that group goes
@@ -453,6 +454,7 @@ struct SoftRing {
     }
     __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
         base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * PB;
+        gbase = static_cast<const unsigned char*>(warp_smem) + lane * PB;
         T = steps; nextp = row; next_t = 0; woff = 0; roff = 0;
         one = __uint_as_float(0x3f800000u | (steps >> 31));          // steps < 2^31: exactly 1.0f and -0.0f
         negzero = __uint_as_float(0x80000000u | (steps >> 31));
@@ -482,9 +484,14 @@ struct SoftRing {
             float bm[M];
             static_for<0, M / 4>([&](auto qc) {
                 constexpr int Q = decltype(qc)::value;
-                asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
-                             : "=f"(bm[4 * Q]), "=f"(bm[4 * Q + 1]), "=f"(bm[4 * Q + 2]), "=f"(bm[4 * Q + 3])
-                             : "r"(a), "n"(elem_off<PH>(4 * Q)));
+                if constexpr (VDEC_OPERAND_V4 == 2) {      // plain load: the compiler may hoist it away from its consumers
+                    const float4 v = *reinterpret_cast<const float4*>(gbase + roff + elem_off<PH>(4 * Q));
+                    bm[4 * Q] = v.x; bm[4 * Q + 1] = v.y; bm[4 * Q + 2] = v.z; bm[4 * Q + 3] = v.w;
+                } else {
+                    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                                 : "=f"(bm[4 * Q]), "=f"(bm[4 * Q + 1]), "=f"(bm[4 * Q + 2]), "=f"(bm[4 * Q + 3])
+                                 : "r"(a), "n"(elem_off<PH>(4 * Q)));
+                }
             });
             // Each half of an operand pair is a COPY of a metric made by an exact identity on the FMA pipes,
             // x * 1.0 + (-0.0) = x for every x (one, negzero: run-time values the compiler cannot fold), written

@@ -26,8 +26,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t
                                               uint32_t (&o)[4]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t hi0, lo0, hi1, lo1;                  // one IMAD.WIDE per product instead of IMAD + IMAD.HI
+        asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(0xD2511F53u));
+        asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(0xCD9E8D57u));
         const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
         c0 = n0; c1 = n1; c2 = n2; c3 = n3;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
@@ -78,6 +79,15 @@ __device__ __forceinline__ uint32_t label_of(uint32_t win, uint32_t K, const uin
 // input bits of a frame up to bit t (t at position 0, t-i at position i; bits outside [0, L) read as zero)
 __device__ __forceinline__ uint32_t input_window(const uint8_t* __restrict__ pl, uint32_t t, uint32_t L, uint32_t pb) {
     const int j = (int)(t >> 3);                                  // byte holding bit t
+    if ((pb & 3u) == 0 && (L & 7u) == 0) {
+        // rows are whole 32-bit words and whole bytes (L = 1024: 128 B): two aligned word loads, bytes in stream order
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pl);
+        const int wi = j >> 2;
+        const uint32_t hi = wi >= 1 ? __byte_perm(__ldg(pw + wi - 1), 0, 0x0123) : 0u;       // bytes 4wi-4 .. 4wi-1, big-endian
+        const uint32_t lo = (uint32_t)wi < (pb >> 2) ? __byte_perm(__ldg(pw + wi), 0, 0x0123) : 0u;
+        // 64-bit stream word: bit index 32(wi-1) at position 63; bit t sits at position 31 - (t & 31)
+        return __funnelshift_r(lo, hi, 31u - (t & 31u));
+    }
     uint32_t w = 0;                                               // bits 8(j-2) .. 8j+7, bit 8(j-2) at position 23
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
@@ -103,8 +113,10 @@ __device__ __forceinline__ void noisy_point(const float* s_c, uint32_t sym, uint
     // random bits where they matter (small u1 = large noise: the tail reaches 6.7 sigma)
     const float u1 = __fmaf_rn(__uint2float_rn(w0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     const float ang = __fmaf_rn(__uint2float_rn(w1 >> 8), 3.7450702e-7f, -3.14159265f);      // [-pi, pi)
-    float r2 = fmaxf(-2.0f * __logf(u1), 0.0f), rad;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(rad) : "f"(r2));
+    float lg, rad;                                                                            // u1 >= 2^-33: no denormals in sight
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+    const float r2 = fmaxf(lg * -1.3862943611198906f, 0.0f);                                  // -2 ln u1
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(r2));
     const float sr = sigma * rad;
     x = __fmaf_rn(sr, __cosf(ang), s_c[2 * sym]);                                             // main.c:100-102
     y = __fmaf_rn(sr, __sinf(ang), s_c[2 * sym + 1]);
