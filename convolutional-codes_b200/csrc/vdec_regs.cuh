@@ -45,6 +45,12 @@
 #ifndef VDEC_OPERAND_V4
 #define VDEC_OPERAND_V4 1
 #endif
+// First-wave stagger (see vit_regs_kernel): SM clocks per trellis step by which the resident CTAs of an SM are spread
+// over one CTA lifetime; 0 = off.  Same-box A/B (profiles/r02g_ab_stagger.txt): K = 7 reference labels 119.4 -> 122.0
+// Gbit/s, rate 1/3 74.9 -> 76.2, true-parity rate 1/2 99.3 -> 98.5 (stays off there).
+#ifndef VDEC_STAGGER
+#define VDEC_STAGGER 670
+#endif
 
 namespace vd {
 
@@ -57,6 +63,7 @@ struct CodeDef {
     // 5 % faster with 168 registers and 3 CTAs; the reference-labelled (171,133) code prefers 4.
     static constexpr int kMinBlocks = (K_ == 7 && !(N_ == 2 && REF_)) ? VDEC_MINB_LIN : VDEC_MINB_REF;
     static constexpr bool kSignDecisions = (N_ == 2 && (REF_ || VDEC_SIGN_LIN));      // survivor bits from packed differences, see kDecSign
+    static constexpr int kStagger = (K_ == 7 && (REF_ || N_ == 3)) ? VDEC_STAGGER : 0;  // first-wave stagger, see VDEC_STAGGER
     VDEC_HD static constexpr uint32_t label(uint32_t s, uint32_t i) {
         const uint64_t p[3] = {P0_, P1_, P2_};
         return branch_label(K_, N_, p, REF_, s, i);
@@ -420,7 +427,6 @@ struct SoftRing {
     uint32_t base;        // shared-window address of this lane's first piece
     uint32_t T;
     float one, negzero;   // 1.0f and -0.0f as run-time values (get_pairs)
-    const unsigned char* gbase;   // generic address of this lane's first piece (VDEC_OPERAND_V4 == 2)
     const float* nextp;   // first step of the next group to prefetch (this lane's frame row)
     uint32_t next_t;      // its step index
     uint32_t woff;        // ring byte offset where that group goes
@@ -454,7 +460,6 @@ struct SoftRing {
     }
     __device__ __forceinline__ void init(void* warp_smem, uint32_t lane, const float* row, uint32_t steps) {
         base = (uint32_t)__cvta_generic_to_shared(warp_smem) + lane * PB;
-        gbase = static_cast<const unsigned char*>(warp_smem) + lane * PB;
         T = steps; nextp = row; next_t = 0; woff = 0; roff = 0;
         one = __uint_as_float(0x3f800000u | (steps >> 31));          // steps < 2^31: exactly 1.0f and -0.0f
         negzero = __uint_as_float(0x80000000u | (steps >> 31));
@@ -484,14 +489,9 @@ struct SoftRing {
             float bm[M];
             static_for<0, M / 4>([&](auto qc) {
                 constexpr int Q = decltype(qc)::value;
-                if constexpr (VDEC_OPERAND_V4 == 2) {      // plain load: the compiler may hoist it away from its consumers
-                    const float4 v = *reinterpret_cast<const float4*>(gbase + roff + elem_off<PH>(4 * Q));
-                    bm[4 * Q] = v.x; bm[4 * Q + 1] = v.y; bm[4 * Q + 2] = v.z; bm[4 * Q + 3] = v.w;
-                } else {
-                    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
-                                 : "=f"(bm[4 * Q]), "=f"(bm[4 * Q + 1]), "=f"(bm[4 * Q + 2]), "=f"(bm[4 * Q + 3])
-                                 : "r"(a), "n"(elem_off<PH>(4 * Q)));
-                }
+                asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                             : "=f"(bm[4 * Q]), "=f"(bm[4 * Q + 1]), "=f"(bm[4 * Q + 2]), "=f"(bm[4 * Q + 3])
+                             : "r"(a), "n"(elem_off<PH>(4 * Q)));
             });
             // Each half of an operand pair is a COPY of a metric made by an exact identity on the FMA pipes,
             // x * 1.0 + (-0.0) = x for every x (one, negzero: run-time values the compiler cannot fold), written
@@ -646,6 +646,20 @@ vit_regs_kernel(const typename MP::In* __restrict__ in, uint8_t* __restrict__ ou
     const size_t warp_smem = ring_bytes > tile_bytes ? ring_bytes : tile_bytes;
     unsigned char* my_smem = s_raw + warp * warp_smem;
 
+    // All CTAs of a wave start together, run the same number of steps and therefore reach their (latency-bound,
+    // low-issue) traceback together: the SM then has nothing to overlap it with.  The CTAs that share an SM in the
+    // FIRST wave are started a fraction of a CTA lifetime apart, once; the phase shift persists for the rest of the
+    // grid, so that a traceback always runs next to three forward passes.
+    if constexpr (CD::kStagger > 0 && MP::kPacked) {
+        constexpr uint32_t kSlots = (uint32_t)CD::kMinBlocks;
+        uint32_t nsm;
+        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        const uint32_t slot = blockIdx.x / nsm;                       // first wave: CTAs are dealt out one per SM, round after round
+        if (slot > 0 && slot < kSlots && gridDim.x > 2 * kSlots * nsm) {
+            const long long until = clock64() + (long long)slot * T * (CD::kStagger / (int)kSlots);
+            while (clock64() < until) __nanosleep(2000);
+        }
+    }
     Feeder feed;
     feed.init(my_smem, lane, in + (size_t)fr * stride_steps * step_elems, T);
 
