@@ -170,11 +170,8 @@ static int decode_geom(vdec_priv* p, int slot, const vd::LaunchGeom& geom, const
         else if (h->regs) rc = h->regs->launch(g, in, out, pm, p->sc.p[slot], st);
         else rc = vd::generic_launch(g, h->cfg.metric, h->bfly_labels_dev, in, out, pm, p->sc.p[slot], st);
         if (rc != 0) return -1;
-        // register kernels: one launch; table-driven and register-tile kernels: forward + traceback, except the small
-        // fp32 tile configurations that walk back inside the forward kernel
-        const bool fused_tile = (h->tile || (h->jit && vd::jit_family(h->jit) == vd::kJitTile)) && g.K <= 9;
-        h->launches += fused_tile ? 1 : h->jit ? vd::jit_launches(h->jit)
-                                : (!h->tile && !h->tile2 && (h->regs || h->regs2 || h->regsw)) ? 1 : 2;
+        h->launches += h->jit ? vd::jit_launches(h->jit)
+                                : (!h->tile && !h->tile2 && (h->regs || h->regs2 || h->regsw)) ? 1 : 2;   // tile, table-driven = forward + traceback
         done += n;
     }
     return 0;

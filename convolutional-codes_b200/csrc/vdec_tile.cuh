@@ -49,18 +49,6 @@ VDEC_HD constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return
 #define VDEC_TILE_TM_MAX 128
 #endif
 VDEC_HD constexpr bool tile_thread_major(uint32_t tpf) { return tpf >= VDEC_TILE_TM_MIN && tpf <= VDEC_TILE_TM_MAX; }
-// Traceback inside the forward kernel for frames of at most this many threads (K <= 9 by default): the separate
-// traceback pass is a full re-read of the survivor array at HBM speed (K = 9: 4.3 GB, 0.89 of 7.1 ms) that nothing
-// overlaps; inside the kernel one thread per frame walks back while the SM's other CTA keeps computing.
-#ifndef VDEC_TILE_FUSE_TB_MAX
-#define VDEC_TILE_FUSE_TB_MAX 4          // threads per frame: K <= 9 (vdec_api.cu counts launches with the same rule)
-#endif
-VDEC_HD constexpr bool tile_fused_traceback(uint32_t tpf) { return tpf <= VDEC_TILE_FUSE_TB_MAX; }
-// ... which only pays when the two resident CTAs of an SM are out of phase: the second CTA of the first wave starts
-// this many SM clocks per trellis step later (about half a CTA lifetime), once; 0 = off
-#ifndef VDEC_TILE_STAGGER
-#define VDEC_TILE_STAGGER 850
-#endif
 
 // N_ = 3 (rate 1/3, 8 metrics per step, third polynomial P2_): true-parity labels only — the de-facto labelling would
 // need a 64-letter extended alphabet.
@@ -77,7 +65,6 @@ struct TileDef {
     static constexpr int FPC = kTileThreads / TPF;            // frames per CTA
     static constexpr bool kThreadMajor = tile_thread_major(TPF);   // survivor layout, see VDEC_TILE_TM_MIN / _MAX
     static constexpr bool kSign = K_ >= 9;                    // sign-based decisions (vdec_regs.cuh kDecSign): K = 8 loses 7 % with them
-    static constexpr bool kFusedTb = tile_fused_traceback(TPF); // traceback at the end of the forward kernel
     static constexpr int RT = TPF > 32 ? TPF : 32;            // threads sharing one exchange region
     static constexpr int RTB = ilog2(RT);
     static constexpr int E = 6 + RTB;                         // address bits of a region (RT * 64 floats)
@@ -232,14 +219,10 @@ constexpr int kTileRingGroups = 3;                                  // windows o
 VDEC_HD constexpr int tile_ring_bytes(int n) { return kTileRingGroups * 6 * (4 << n); }     // per frame
 constexpr int kTileVmBytes = 6 * 16 * 4;                            // per frame: one window of metrics expanded by extended label
 
-// one frame's traceback (defined below, next to the stand-alone traceback kernel)
-template <bool THREAD_MAJOR, bool SIGN, bool PREFETCH>
-__device__ __forceinline__ void tile_walk(const uint2* __restrict__ sv, uint32_t h, uint8_t* __restrict__ row, uint32_t T, uint32_t B, uint32_t TPF);
-
 template <class TD>
 __global__ void __launch_bounds__(kTileThreads, 2)
 vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_t* __restrict__ final_state,
-                 uint32_t nframes, uint32_t T, uint32_t stride_steps, uint32_t init_all_from, uint8_t* __restrict__ out, uint32_t out_bytes) {
+                 uint32_t nframes, uint32_t T, uint32_t stride_steps, uint32_t init_all_from) {
     constexpr int B = TD::B, S = TD::S, TB = TD::TB, TPF = TD::TPF, FPC = TD::FPC, RT = TD::RT;
     extern __shared__ __align__(1024) unsigned char s_raw[];
     float* xall = reinterpret_cast<float*>(s_raw);                               // [NREG][RT * 64] exchange regions
@@ -254,14 +237,6 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t tau = tid & (TPF - 1), fic = tid / TPF;
-    if constexpr (TD::kFusedTb && VDEC_TILE_STAGGER > 0) {
-        uint32_t nsm;
-        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-        if (blockIdx.x >= nsm && blockIdx.x < 2 * nsm && gridDim.x > 4 * nsm) {     // first wave, second CTA of each SM
-            const long long until = clock64() + (long long)T * VDEC_TILE_STAGGER;
-            while (clock64() < until) __nanosleep(2000);
-        }
-    }
     const uint32_t f = blockIdx.x * FPC + fic;
     const bool live = f < nframes;
     const uint32_t fr = live ? f : nframes - 1;                                 // dead groups shadow the last frame
@@ -410,16 +385,6 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
         }
     }
     if (live && tau == 0) final_state[f] = (bs == 0xFFFFFFFFu) ? 0u : bs;
-    if constexpr (TD::kFusedTb) {
-        // ---- traceback inside the kernel: frame i of the CTA is walked by thread i (the first FPC / 32 warps); the
-        // CTA's survivor words and final states are its own global writes, visible to all its threads after the barrier
-        __syncthreads();
-        if (tid < (uint32_t)FPC) {
-            const uint32_t fw = blockIdx.x * FPC + tid;
-            if (fw < nframes)
-                tile_walk<TD::kThreadMajor, TD::kSign, true>(surv + (size_t)fw * T * TPF, __ldcg(final_state + fw), out + (size_t)fw * out_bytes, T, (uint32_t)B, (uint32_t)TPF);
-        }
-    }
 }
 
 // ONE THREAD PER FRAME.  At the window's k-th step the decision of state `cur` is bit
@@ -427,20 +392,19 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
 // the same for every step of a window, so a window's words are fetched together.  Output as in vdec_regs.cuh:
 // the state doubles as a shift register of decoded bits, 16 of which are emitted every 16 steps (:81-89).
 // THREAD_MAJOR: survivor layout [frame][thread][step] (tile_thread_major); SIGN: rotated survivor-bit layout (TileDef::kSign)
-template <bool THREAD_MAJOR, bool SIGN, bool PREFETCH>
-__device__ __forceinline__ void tile_walk(const uint2* __restrict__ sv, uint32_t h, uint8_t* __restrict__ row, uint32_t T, uint32_t B, uint32_t TPF) {
+template <bool THREAD_MAJOR, bool SIGN>
+static __global__ void __launch_bounds__(128)
+vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ final_state, uint8_t* __restrict__ out,
+                   uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t B, uint32_t TPF) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes) return;
+    const uint2* sv = surv + (size_t)f * T * TPF;
+    uint8_t* row = out + (size_t)f * out_bytes;
     const uint32_t S1 = (1u << B) - 1u;
+    uint32_t h = final_state[f];
     for (int w0 = (int)((T - 1) / 6) * 6; w0 >= 0; w0 -= 6) {
         const int n = (int)T - w0 < 6 ? (int)T - w0 : 6;
         const uint32_t owner = ((h & S1) >> (6 - n)) & (TPF - 1);
-        if constexpr (PREFETCH && !THREAD_MAJOR) {
-            // step-major records: whichever thread's words the walk will need, they lie in the 6 * TPF * 8 contiguous
-            // bytes of the window, so the windows further back can be pulled into L2 before their owner is known
-            if (w0 >= 48) {
-                const char* pw = reinterpret_cast<const char*>(sv + (size_t)(w0 - 48) * TPF);
-                for (uint32_t o = 0; o < 6u * TPF * 8u; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + o));
-            }
-        }
         uint2 wd[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k)
@@ -461,15 +425,6 @@ __device__ __forceinline__ void tile_walk(const uint2* __restrict__ sv, uint32_t
             h = (h << 1) | ((word >> (bit & 31u)) & 1u);                 // predecessor (:86)
         }
     }
-}
-
-template <bool THREAD_MAJOR, bool SIGN>
-static __global__ void __launch_bounds__(128)
-vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ final_state, uint8_t* __restrict__ out,
-                   uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t B, uint32_t TPF) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nframes) return;
-    tile_walk<THREAD_MAJOR, SIGN, false>(surv + (size_t)f * T * TPF, final_state[f], out + (size_t)f * out_bytes, T, B, TPF);
 }
 
 #ifndef __CUDACC_RTC__
@@ -499,10 +454,9 @@ inline int tile_launch_kernel(const void* kern, const TileShape& sh, const Launc
     VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t blocks = (g.nframes + sh.FPC - 1) / sh.FPC;
     const float* inf = static_cast<const float*>(in);
-    uint32_t nframes = g.nframes, T = g.T, stride = g.stride_steps, init_all_from = g.init_all_from, out_bytes = g.out_bytes;
-    void* args[] = {&inf, &surv, &final_state, &nframes, &T, &stride, &init_all_from, &out, &out_bytes};
+    uint32_t nframes = g.nframes, T = g.T, stride = g.stride_steps, init_all_from = g.init_all_from;
+    void* args[] = {&inf, &surv, &final_state, &nframes, &T, &stride, &init_all_from};
     VDEC_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kTileThreads), args, smem, st));
-    if (tile_fused_traceback(sh.TPF)) return 0;                   // the forward kernel walked back itself
     const uint32_t tb_blocks = (g.nframes + 127) / 128;
     const bool tm = tile_thread_major(sh.TPF);
     if (tm && sh.sign) vit_tile_traceback<true, true><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
