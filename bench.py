@@ -360,22 +360,28 @@ def run_gpu(args) -> int:
     iq_kernel = dec.iq_kernel_name
 
     # ---- bare pinned host -> device bandwidth, all ranks at once: the ceiling of every host-buffer number below
-    hb = torch.empty((256 << 20,), dtype=torch.uint8, pin_memory=True)
-    hb.fill_(1)                                              # first touch on this rank's CPUs
-    db = torch.empty_like(hb, device=dev)
-    db.copy_(hb, non_blocking=True)
-    barrier()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h0.record()
-    for _ in range(8):
-        db.copy_(hb, non_blocking=True)                     # cudaMemcpyAsync, 256 MiB each
-    h1.record()
-    torch.cuda.synchronize()
-    th2d = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(th2d, op=dist.ReduceOp.MAX)
-    h2d_peak_gbs = world * 8 * hb.numel() / (float(th2d.item()) * 1e-3) / 1e9
-    del hb, db
+    def h2d_peak():
+        hb = torch.empty((256 << 20,), dtype=torch.uint8, pin_memory=True)
+        hb.fill_(1)                                              # first touch on this rank's CPUs
+        db = torch.empty_like(hb, device=dev)
+        best = None
+        for _ in range(3):                                       # best of three series (the first one after a kernel phase can run slow)
+            db.copy_(hb, non_blocking=True)
+            barrier()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(8):
+                db.copy_(hb, non_blocking=True)                 # cudaMemcpyAsync, 256 MiB each
+            h1.record()
+            torch.cuda.synchronize()
+            th2d = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(th2d, op=dist.ReduceOp.MAX)
+            gbs = world * 8 * hb.numel() / (float(th2d.item()) * 1e-3) / 1e9
+            best = gbs if best is None else max(best, gbs)
+        return best
+
+    h2d_peak_gbs = h2d_peak()
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H in the timed region
     Fe = min(args.e2e_frames, F)
@@ -531,7 +537,7 @@ def run_gpu(args) -> int:
         "e2e": {"value": e2e_gbit, "unit": UNIT, "h2d_bytes_per_step": Fe * dec.in_bytes, "d2h_bytes_per_step": Fe * dec.out_bytes,
                 "frames_per_step": Fe, "api": "vdec_decode_host (pinned host buffers, 2-stream pipeline)",
                 "h2d_gbs": e2e_h2d_gbs, "h2d_peak_gbs": h2d_peak_gbs, "frac_of_h2d_peak": e2e_h2d_gbs / h2d_peak_gbs,
-                "h2d_peak_how": f"{world} rank(s) at once, 8 x cudaMemcpyAsync of 256 MiB from pinned host memory, nothing else running",
+                "h2d_peak_how": f"{world} rank(s) at once, 8 x cudaMemcpyAsync of 256 MiB from pinned host memory, nothing else running, best of 3 series",
                 "cpu_affinity": affinity},
         "e2e_iq": {"value": e2e_iq_gbit, "unit": UNIT, "h2d_bytes_per_step": Fe * code.T * 8, "d2h_bytes_per_step": Fe * dec.out_bytes,
                    "frames_per_step": Fe, "h2d_gbs": e2e_iq_h2d_gbs, "frac_of_h2d_peak": e2e_iq_h2d_gbs / h2d_peak_gbs, "kernel": iq_kernel,
