@@ -37,7 +37,7 @@ def main():
     failures = []
     while time.time() < t_end:
         K = int(rng.integers(3, 13))
-        n = int(rng.choice([2, 2, 3]))
+        n = int(rng.choice([1, 2, 2, 2, 3, 3]))
         L = int(rng.choice([1, 2, 7, 40, 97, 249, 300, 1024])) if rng.random() < 0.5 else int(rng.integers(1, 400))
         if K >= 11:
             L = min(L, 200)
@@ -69,6 +69,17 @@ def main():
                     exp = orc.decode_soft(oc, q.astype(np.float32))
                     dec = cc.BatchDecoder(code, metric, parity, flags=flags, metric_max=qmax)
                     o = dec.decode(torch.from_numpy(q).cuda())
+                elif rng.random() < 0.35:
+                    # raw-I/Q entry: demapper inside the decoder kernel (register kernels) or demap kernel + decoder
+                    cst = orc.constellation(n)
+                    r2 = np.random.default_rng(seed)
+                    pl = r2.integers(0, 256, size=(F, oc.payload_bytes), dtype=np.uint8)
+                    iq = cst[orc.encode(oc, pl)].astype(np.float32) + (float(rng.choice([0.0, 0.3, 0.8])) * r2.standard_normal((F, oc.T, 2))).astype(np.float32)
+                    exp = orc.decode_soft(oc, orc.demap(n, iq.reshape(-1, 2)).reshape(F, oc.T, oc.M))
+                    dec = cc.BatchDecoder(code, metric, parity, flags=flags)
+                    o = dec.decode_iq(torch.from_numpy(np.ascontiguousarray(iq)).cuda())
+                    case["entry"] = "iq: " + dec.iq_kernel_name.split("<")[0]
+                    stats["iq_cases"] += 1
                 else:
                     exp = orc.decode_soft(oc, met)
                     dec = cc.BatchDecoder(code, metric, parity, flags=flags)
