@@ -193,3 +193,25 @@ def test_unmodified_bsc_driver_runs_on_gpu():
     except subprocess.TimeoutExpired as e:
         out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
     assert "Channel error rate: 0.000001" in out and "Error:" not in out, out[-300:]
+
+
+def test_c_sweep_driver_binary(cc, tmp_path):
+    """examples/vdec_sweep_main.c (built as lib/vdec-sweep): the reference drivers' operating-point loop in plain C on
+    top of vdec_sweep().  Its printed counters equal the library call's, and the Octave vectors carry the GPU count."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "convolutional-codes_b200", "lib", "vdec-sweep")
+    assert os.path.exists(exe), "run `python __graft_entry__.py build`"
+    out_m = str(tmp_path / "sweep.m")
+    r = subprocess.run([exe, "--code", "cb3", "--ebn0", "2:6:2", "--frames", "60000", "--gpus", "1", "--seed", "99", "--out", out_m],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-400:]
+    got = [[int(x) for x in m] for m in re.findall(r"bits (\d+)  bit errors (\d+)  frame errors (\d+)", r.stdout)]
+    exp = cc.sweep(cc.get_code(3), [2.0, 4.0, 6.0], 60000, cc.CHANNEL_AWGN, cc.PARITY_REF, seed=99, ndev=1)
+    assert got == exp.tolist(), (got, exp.tolist())
+    assert len(re.findall(r"Overall transmission error rate: [0-9.]+", r.stdout)) == 3          # the drivers' wording, main.c:233
+    text = open(out_m).read()
+    assert "n_gpus_cb3_ref_soft = 1;" in text and "ber_cb3_ref_soft = [" in text and "snr_cb3_ref_soft = [2 4 6];" in text
+    # the 17 channel error rates of the BSC driver
+    r = subprocess.run([exe, "--code", "cb0", "--channel", "bsc", "--frames", "20000", "--gpus", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.count("Channel error rate:") == 17, r.stdout[-300:]

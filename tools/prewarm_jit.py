@@ -5,6 +5,7 @@ snapshot like the built .so files), so a GPU run spends its time decoding instea
     python tools/prewarm_jit.py [-j 8]"""
 import argparse
 import os
+import shutil
 import sys
 from concurrent.futures import ProcessPoolExecutor
 
@@ -52,11 +53,33 @@ def run(job):
         return job, repr(e)
 
 
+def _sources_digest() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "convolutional-codes_b200", "csrc")
+    for n in sorted(os.listdir(d)):
+        if n.endswith((".cuh", ".h")):
+            h.update(open(os.path.join(d, n), "rb").read())
+    h.update(open(os.path.join(ROOT, "include", "vdec.h"), "rb").read())
+    h.update(open(os.path.join(ROOT, "convolutional-codes_b200", "_build.py"), "rb").read())
+    return h.hexdigest()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("-j", type=int, default=min(8, os.cpu_count() or 1))
+    ap.add_argument("--keep", action="store_true", help="do not drop cache entries of other source versions")
     args = ap.parse_args()
+    # the cache key hashes the kernel headers: entries of earlier source versions are dead weight in the GPU-box
+    # snapshot, so the directory is rebuilt from scratch unless every job is already served from it (--keep)
+    if not args.keep and os.path.isdir(CACHE):
+        stamp = os.path.join(CACHE, ".sources")
+        cur = _sources_digest()
+        if not os.path.exists(stamp) or open(stamp).read() != cur:
+            shutil.rmtree(CACHE)
     os.makedirs(CACHE, exist_ok=True)
+    with open(os.path.join(CACHE, ".sources"), "w") as f:
+        f.write(_sources_digest())
     with ProcessPoolExecutor(args.j) as ex:
         res = list(ex.map(run, jobs()))
     bad = [r for r in res if not isinstance(r[1], int)]
