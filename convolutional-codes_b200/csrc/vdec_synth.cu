@@ -250,18 +250,24 @@ count_errors_kernel(const uint8_t* __restrict__ dec, const uint8_t* __restrict__
     const uint32_t last_mask = (L & 7) ? ((0xFF00u >> (L & 7)) & 0xFFu) : 0xFFu;      // only the first L bits count
     const uint64_t f0 = ((uint64_t)blockIdx.x * (kCountThreads / 32) + warp) * kCountFrames;
     uint32_t errs = 0, ferr = 0;
-    for (int k = 0; k < kCountFrames; ++k) {
+    uint32_t e[kCountFrames];
+#pragma unroll
+    for (int k = 0; k < kCountFrames; ++k) {                    // all loads of the warp's frames in flight together
         const uint64_t f = f0 + k;
-        if (f >= nframes) break;
-        const uint8_t* d = dec + f * out_bytes; const uint8_t* p = payload + f * pb;
-        uint32_t e = 0;
-        for (uint32_t j = lane; j < pb; j += 32) {
-            uint32_t x = (uint32_t)(__ldg(d + j) ^ __ldg(p + j));
-            if (j == pb - 1) x &= last_mask;
-            e += __popc(x);
+        e[k] = 0;
+        if (f < nframes) {
+            const uint8_t* d = dec + f * out_bytes; const uint8_t* p = payload + f * pb;
+            for (uint32_t j = lane; j < pb; j += 32) {
+                uint32_t x = (uint32_t)(__ldg(d + j) ^ __ldg(p + j));
+                if (j == pb - 1) x &= last_mask;
+                e[k] += __popc(x);
+            }
         }
-        e = __reduce_add_sync(0xffffffffu, e);
-        errs += e; ferr += e ? 1u : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kCountFrames; ++k) {
+        const uint32_t t = __reduce_add_sync(0xffffffffu, e[k]);
+        errs += t; ferr += t ? 1u : 0u;
     }
     if (lane == 0) { s_err[warp] = errs; s_ferr[warp] = ferr; }
     __syncthreads();
