@@ -48,6 +48,35 @@ constexpr uint32_t kRegs2Limit = 0x4000u;     // T * max branch metric must stay
 
 enum { kModeHard = 0, kModeQuant = 1 };
 
+// Hard decisions: the M packed Hamming metrics of a step depend on the two received n-bit symbols only, so they come
+// out of a shared-memory table indexed by (symbol A, symbol B) — one LDS.128 (two for n = 3) instead of 16 - 28 ALU-pipe
+// operations per step.  That is 6 % of a K = 7 step but 30 - 40 % of a step on the 4- and 8-state trellises of the
+// codebook, where the per-step overhead is shared by very few butterflies (profiles/r02q_ab_hard_lut.txt).
+#ifndef VDEC_HARD_LUT
+#define VDEC_HARD_LUT 1
+#endif
+template <int N> constexpr int kHardLutWords = (1 << (2 * N)) * (1 << N);
+template <int N>
+__device__ __forceinline__ void hard_lut_init(uint32_t* lut) {
+    constexpr int M = 1 << N;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)kHardLutWords<N>; i += blockDim.x) {
+        const uint32_t e = i & (M - 1), ra = (i >> N) & (M - 1), rb = i >> (2 * N);
+        lut[i] = (uint32_t)__popc(e ^ ra) | ((uint32_t)__popc(e ^ rb) << 16);          // :69-72 for both frames
+    }
+    __syncthreads();
+}
+template <int N>
+__device__ __forceinline__ void hard_lut_bm(const uint32_t* lut, uint2 x, uint32_t (&bm)[1 << N]) {
+    constexpr int M = 1 << N;
+    const uint32_t idx = (x.x & (M - 1)) | ((x.y & (M - 1)) << N);                       // :235-237, both frames
+    const uint4* row = reinterpret_cast<const uint4*>(lut + idx * M);
+    if constexpr (M == 2) { const uint2 v = *reinterpret_cast<const uint2*>(lut + idx * 2); bm[0] = v.x; bm[1] = v.y; }
+    else {
+#pragma unroll
+        for (int q = 0; q < M / 4; ++q) { const uint4 v = row[q]; bm[4 * q] = v.x; bm[4 * q + 1] = v.y; bm[4 * q + 2] = v.z; bm[4 * q + 3] = v.w; }
+    }
+}
+
 // branch metrics of one step for both frames, packed: bm[e] = mA(e) | mB(e) << 16
 template <int M, int MODE>
 __device__ __forceinline__ void packed_bm(uint2 x, uint32_t (&bm)[M]) {
@@ -170,6 +199,9 @@ vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t
     constexpr int S = CD::S, B = CD::B, M = CD::M, NW = Surv2<S>::NW;
     using SV = typename SurvVec<NW>::type;
     extern __shared__ __align__(16) unsigned char s_raw[];      // output staging: [warp][64 rows][out_bytes], tile_bytes per warp
+    constexpr bool kLut = VDEC_HARD_LUT && MODE == kModeHard;
+    __shared__ __align__(16) uint32_t s_lut[kLut ? kHardLutWords<CD::N> : 4];
+    if constexpr (kLut) hard_lut_init<CD::N>(s_lut);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t gt = blockIdx.x * kRegsThreads + tid;        // thread <-> frames 2*gt, 2*gt+1
@@ -205,7 +237,8 @@ vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t
             constexpr int PH = decltype(phc)::value;
             const uint2 x = xn;
             xn = fetch(min(t + PH + 1, T - 1));                                // one step of lookahead
-            packed_bm<M, MODE>(x, bm);
+            if constexpr (kLut) hard_lut_bm<CD::N>(s_lut, x, bm);
+            else packed_bm<M, MODE>(x, bm);
             acs_step2<CD, PH>(r, bm, dw);
             store_dw(t + PH);
         });
@@ -216,7 +249,8 @@ vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t
         if (PH < (int)rem) {
             const uint2 x = xn;
             xn = fetch(min(t + PH + 1, T - 1));                                // one step of lookahead
-            packed_bm<M, MODE>(x, bm);
+            if constexpr (kLut) hard_lut_bm<CD::N>(s_lut, x, bm);
+            else packed_bm<M, MODE>(x, bm);
             acs_step2<CD, PH>(r, bm, dw);
             store_dw(t + PH);
         }
