@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "vdec_internal.h"
@@ -79,6 +80,7 @@ struct Dev {
 // communicators are created once per device list and kept for the life of the process (ncclCommInitAll costs ~1 s)
 struct CommSet { std::vector<int> ids; std::vector<ncclComm_t> comm; };
 std::vector<CommSet> g_comms;
+std::mutex g_sweep_mu;                 // one sweep at a time per process: the communicators and their streams are shared
 
 struct Sweep {
     std::vector<Dev> dev;
@@ -122,6 +124,7 @@ extern "C" int vdec_sweep(const struct vdec_config* cfg, const struct vdec_sweep
     if ((cfg->metric == VDEC_HARD_U16) != bsc) { set_error("vdec_sweep: the BSC channel needs VDEC_HARD_U16, the AWGN channels VDEC_SOFT_F32"); return -1; }
     if (!bsc && cfg->metric != VDEC_SOFT_F32) { set_error("vdec_sweep: the AWGN channels need VDEC_SOFT_F32"); return -1; }
 
+    std::lock_guard<std::mutex> lock(g_sweep_mu);
     Sweep s;
     s.dev.resize(ndev);
     // frames per launch and device: four full waves of the register kernels (148 SMs x 4 CTAs x 128 frames)

@@ -198,7 +198,8 @@ int vdec_synth_bsc_device(vdec_t* h, uint64_t nframes, uint64_t first_frame, uin
  *   points[i]      Eb/N0 in dB (AWGN channels, sigma as main.c:153-161) or the crossover rate in ppm (BSC, main.c:103-109)
  *   devices        CUDA ordinals, NULL = 0 .. ndev-1; ndev = 0: every device present
  *   counters_out   [npoints][3] = bits compared, bit errors, frames in error (main.c:129-141)
- * cfg->metric must be VDEC_SOFT_F32 for the AWGN channels and VDEC_HARD_U16 for the BSC; cfg->device is ignored. */
+ * cfg->metric must be VDEC_SOFT_F32 for the AWGN channels and VDEC_HARD_U16 for the BSC; cfg->device is ignored.
+ * Calls from several host threads are serialised (the NCCL communicators are created once per device list and kept). */
 enum vdec_channel {
     VDEC_CHANNEL_AWGN = 0,        /* soft demapper (common/demapper.c), fused into the decoder where the kernel family allows */
     VDEC_CHANNEL_AWGN_HARD = 1,   /* hard demapper (common/hard-demapper.c): the `*_h` curves */
