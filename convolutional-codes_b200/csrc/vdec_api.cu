@@ -44,8 +44,10 @@ struct vdec_priv {
     size_t stage_frames;      // capacity of the host pipeline buffers, in frames
     float* met[3];            // demapped-metric staging for the raw-I/Q entry, per scratch slot
     size_t met_frames[3];
-    uint8_t* stream_tmp;      // per-block outputs of the sliding-window decoder before stitching
-    size_t stream_tmp_bytes;
+    uint8_t* stream_tmp[3];   // per-block outputs of the sliding-window decoder before stitching, per scratch slot
+    size_t stream_tmp_bytes[3];
+    cudaStream_t side[2];     // the first and the last window of a stream run beside the interior windows
+    cudaEvent_t ev_fork, ev_join[2];
     float* iq_dev[2];         // device staging of host I/Q, per pipeline stage
     uint8_t* iq_out[2];       // and of the decoded output
     size_t iq_frames;
@@ -372,7 +374,9 @@ void vdec_destroy(vdec_t* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 3; ++i) guarded_free(p, p->sc.p[i]);
     for (int i = 0; i < 3; ++i) guarded_free(p, p->met[i]);
-    guarded_free(p, p->stream_tmp);
+    for (int i = 0; i < 3; ++i) guarded_free(p, p->stream_tmp[i]);
+    for (int i = 0; i < 2; ++i) { if (p->side[i]) cudaStreamDestroy(p->side[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     for (int i = 0; i < 2; ++i) { if (p->iq_dev[i]) cudaFree(p->iq_dev[i]); if (p->iq_out[i]) cudaFree(p->iq_out[i]); }
     for (int i = 0; i < 2; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
@@ -563,7 +567,7 @@ int vdec_decode_iq_host(vdec_t* h, const float* iq_host, uint64_t nframes, uint8
 
 // One window launch of the sliding-window decoder: `nblk` blocks of T steps whose starts are `stride` steps apart,
 // decoded into the temporary buffer, then bytes [skip/8, skip/8 + keep_bytes) of each block are appended to `out`.
-static int stream_pass(vdec_priv* p, const uint8_t* in, size_t step_bytes, uint64_t start_step, uint64_t nblk, uint32_t T,
+static int stream_pass(vdec_priv* p, int slot, const uint8_t* in, size_t step_bytes, uint64_t start_step, uint64_t nblk, uint32_t T,
                        uint32_t stride, bool known_first, uint32_t skip_bits, uint64_t keep_bytes, uint64_t last_keep_bytes,
                        uint8_t* out, cudaStream_t st) {
     vdec* h = &p->base;
@@ -572,14 +576,14 @@ static int stream_pass(vdec_priv* p, const uint8_t* in, size_t step_bytes, uint6
     g.T = T; g.L = T - (g.K - 1 < T ? g.K - 1 : 0); g.out_bytes = (T + 7) / 8;
     g.stride_steps = stride; g.init_all_from = known_first ? 1u : 0u;
     const size_t need = nblk * g.out_bytes;
-    if (need > p->stream_tmp_bytes) {
-        if (p->stream_tmp) { guarded_free(p, p->stream_tmp); p->stream_tmp = nullptr; p->stream_tmp_bytes = 0; }
-        VDEC_CUDA(guarded_malloc(p, reinterpret_cast<void**>(&p->stream_tmp), need));
-        p->stream_tmp_bytes = need;
+    if (need > p->stream_tmp_bytes[slot]) {
+        if (p->stream_tmp[slot]) { guarded_free(p, p->stream_tmp[slot]); p->stream_tmp[slot] = nullptr; p->stream_tmp_bytes[slot] = 0; }
+        VDEC_CUDA(guarded_malloc(p, reinterpret_cast<void**>(&p->stream_tmp[slot]), need));
+        p->stream_tmp_bytes[slot] = need;
     }
-    if (decode_geom(p, 0, g, in + start_step * step_bytes, nblk, p->stream_tmp, nullptr, st) != 0) return -1;
+    if (decode_geom(p, slot, g, in + start_step * step_bytes, nblk, p->stream_tmp[slot], nullptr, st) != 0) return -1;
     h->launches += 1;
-    return vd::stitch_launch(p->stream_tmp, g.out_bytes, skip_bits / 8, nblk, keep_bytes, last_keep_bytes, out, st);
+    return vd::stitch_launch(p->stream_tmp[slot], g.out_bytes, skip_bits / 8, nblk, keep_bytes, last_keep_bytes, out, st);
 }
 
 int vdec_stream_decode_device(vdec_t* h, const void* in_dev, uint64_t nsteps, uint32_t block_steps, uint32_t depth,
@@ -602,18 +606,33 @@ int vdec_stream_decode_device(vdec_t* h, const void* in_dev, uint64_t nsteps, ui
     const bool known = (flags & VDEC_STREAM_START_KNOWN) != 0;
     const uint64_t Lb = block_steps, D = depth;
     if (nsteps <= Lb + 2 * D) {                                  // short stream: one window, exact
-        return stream_pass(p, in, step_bytes, 0, 1, (uint32_t)nsteps, (uint32_t)nsteps, known, 0, 0, (nsteps + 7) / 8, out_dev, st);
+        return stream_pass(p, 0, in, step_bytes, 0, 1, (uint32_t)nsteps, (uint32_t)nsteps, known, 0, 0, (nsteps + 7) / 8, out_dev, st);
     }
     const uint64_t nfull = (nsteps - D) / Lb;                    // windows that deliver a full block of Lb bits
+    // The first and the last window are one frame each (a single warp walking > 1000 steps: 0.3 ms of pure latency);
+    // they run on two side streams of the handle, forked from and joined back into the caller's stream, beside the
+    // launch of all interior windows, each with its own scratch slot and staging buffer.
+    for (int i = 0; i < 2; ++i) {
+        if (!p->side[i]) VDEC_CUDA(cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking));
+        if (!p->ev_join[i]) VDEC_CUDA(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+    if (!p->ev_fork) VDEC_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    VDEC_CUDA(cudaEventRecord(p->ev_fork, st));
+    for (int i = 0; i < 2; ++i) VDEC_CUDA(cudaStreamWaitEvent(p->side[i], p->ev_fork, 0));
     // first window: starts with the stream (no warm-up), D steps of look-ahead
-    if (stream_pass(p, in, step_bytes, 0, 1, (uint32_t)(Lb + D), (uint32_t)Lb, known, 0, 0, Lb / 8, out_dev, st) != 0) return -1;
-    // interior windows: D steps warm-up (start state unknown), Lb payload, D look-ahead; starts Lb apart
-    if (nfull > 1 && stream_pass(p, in, step_bytes, Lb - D, nfull - 1, (uint32_t)(Lb + 2 * D), (uint32_t)Lb, false, (uint32_t)D,
-                                 Lb / 8, Lb / 8, out_dev + Lb / 8, st) != 0) return -1;
+    if (stream_pass(p, 1, in, step_bytes, 0, 1, (uint32_t)(Lb + D), (uint32_t)Lb, known, 0, 0, Lb / 8, out_dev, p->side[0]) != 0) return -1;
     // last window: runs to the end of the stream, traced back from the best final state (viterbi-decoder.c:72-79)
     const uint64_t s0 = nfull * Lb - D, rest_bits = nsteps - nfull * Lb;
-    return stream_pass(p, in, step_bytes, s0, 1, (uint32_t)(nsteps - s0), (uint32_t)(nsteps - s0), false, (uint32_t)D, 0,
-                       (rest_bits + 7) / 8, out_dev + nfull * (Lb / 8), st);
+    if (stream_pass(p, 2, in, step_bytes, s0, 1, (uint32_t)(nsteps - s0), (uint32_t)(nsteps - s0), false, (uint32_t)D, 0,
+                    (rest_bits + 7) / 8, out_dev + nfull * (Lb / 8), p->side[1]) != 0) return -1;
+    // interior windows: D steps warm-up (start state unknown), Lb payload, D look-ahead; starts Lb apart
+    if (nfull > 1 && stream_pass(p, 0, in, step_bytes, Lb - D, nfull - 1, (uint32_t)(Lb + 2 * D), (uint32_t)Lb, false, (uint32_t)D,
+                                 Lb / 8, Lb / 8, out_dev + Lb / 8, st) != 0) return -1;
+    for (int i = 0; i < 2; ++i) {
+        VDEC_CUDA(cudaEventRecord(p->ev_join[i], p->side[i]));
+        VDEC_CUDA(cudaStreamWaitEvent(st, p->ev_join[i], 0));
+    }
+    return 0;
 }
 
 long vdec_debug_check(vdec_t* h) {
@@ -625,7 +644,7 @@ long vdec_debug_check(vdec_t* h) {
     long bad = 0;
     unsigned char* host = static_cast<unsigned char*>(malloc(kGuardBytes + 256));
     if (!host) return -1;
-    void* bufs[] = {p->sc.p[0], p->sc.p[1], p->sc.p[2], p->met[0], p->met[1], p->met[2], p->stream_tmp};
+    void* bufs[] = {p->sc.p[0], p->sc.p[1], p->sc.p[2], p->met[0], p->met[1], p->met[2], p->stream_tmp[0], p->stream_tmp[1], p->stream_tmp[2]};
     for (void* u : bufs) {
         if (!u) continue;
         size_t bytes = 0;
