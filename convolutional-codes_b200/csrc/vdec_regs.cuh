@@ -45,6 +45,22 @@
 #ifndef VDEC_OPERAND_V4
 #define VDEC_OPERAND_V4 1
 #endif
+// cp.async.ca (allocate in L1) instead of .cg for the 16-byte pieces of the input ring.  A 32-byte sector holds two
+// pieces (two consecutive steps at n = 2, the two halves of a step at n = 3) and .cg fetches it from L2 once per
+// piece (ncu r02p: 41 KB per frame cross the L2 -> L1 crossbar for 24.7 KB of DRAM reads); with .ca the second
+// request hits L1.  Rate 1/3 needs the ring cut to two groups for that: three groups are 72 KB per CTA, 216 KB per SM,
+// and leave no L1 to hit in (.ca alone: 75.6 -> 65.4 Gbit/s).  Same-box A/B (profiles/r02t_ab_ring_l1_policy.txt):
+// K = 7 reference labels 118.7 - 121.2 -> 123.0 - 123.7, true-parity 98.6 -> 99.6 - 100.4, rate 1/3 75.2 - 76.3 -> 82.2 - 82.4
+// (true-parity labels 77.5 - 78.6 -> 87.6 - 88.6).
+#ifndef VDEC_RING_CA
+#define VDEC_RING_CA 1
+#endif
+#ifndef VDEC_RING_CA_M8
+#define VDEC_RING_CA_M8 1
+#endif
+#ifndef VDEC_RING_NG_M8
+#define VDEC_RING_NG_M8 2        // groups of the rate-1/3 ring
+#endif
 // First-wave stagger (see vit_regs_kernel): SM clocks per trellis step by which the resident CTAs of an SM are spread
 // over one CTA lifetime; 0 = off.  Same-box A/B (profiles/r02g_ab_stagger.txt): K = 7 reference labels 119.4 -> 122.0
 // Gbit/s, rate 1/3 74.9 -> 76.2, true-parity rate 1/2 99.3 -> 98.5 (stays off there).
@@ -415,7 +431,7 @@ struct SoftRing {
     static constexpr int kPieces = kStepBytes / PB;            // pieces per step
     static constexpr int G = B;                                // steps per prefetch group = one rotation period,
                                                                // so the prefetch sits at phase 0 only (no per-step test)
-    static constexpr int NG = 3;                               // groups in the ring
+    static constexpr int NG = (M == 8) ? VDEC_RING_NG_M8 : 3;  // groups in the ring
     static constexpr int kSlots = G * NG;
     static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * kStepBytes;   // K=7, n=2: 9 KB
     static_assert(M == 4 || M == 8, "soft ring feeder supports n = 2, 3");
@@ -434,7 +450,9 @@ struct SoftRing {
 
     template <int OFF_S, int OFF_G>
     static __device__ __forceinline__ void copy_piece(uint32_t dst, const float* src) {
-        if constexpr (PB == 16)
+        if constexpr (PB == 16 && (M == 8 ? VDEC_RING_CA_M8 : VDEC_RING_CA))
+            asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(OFF_S), "n"(OFF_G) : "memory");
+        else if constexpr (PB == 16)
             asm volatile("cp.async.cg.shared.global [%0+%2], [%1+%3], 16;" ::"r"(dst), "l"(src), "n"(OFF_S), "n"(OFF_G) : "memory");
         else
             asm volatile("cp.async.ca.shared.global [%0+%2], [%1+%3], 4;" ::"r"(dst), "l"(src), "n"(OFF_S), "n"(OFF_G) : "memory");
@@ -463,13 +481,12 @@ struct SoftRing {
         T = steps; nextp = row; next_t = 0; woff = 0; roff = 0;
         one = __uint_as_float(0x3f800000u | (steps >> 31));          // steps < 2^31: exactly 1.0f and -0.0f
         negzero = __uint_as_float(0x80000000u | (steps >> 31));
-        prefetch_next();
-        prefetch_next();
+        static_for<0, NG - 1>([&](auto) { prefetch_next(); });
     }
     // start of a period: keep the ring two groups ahead, make the current group visible
     __device__ __forceinline__ void begin_period() {
         prefetch_next();
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(NG - 1) : "memory");
     }
     __device__ __forceinline__ void end_period() { roff = (roff == (NG - 1) * kGroupBytes) ? 0u : roff + kGroupBytes; }
     // ring byte offset (immediate) of metric x of step PH of the current group
@@ -870,7 +887,8 @@ struct RegsShape {
 };
 inline RegsShape regs_shape(uint32_t K, uint32_t n, uint32_t metric, bool iq = false) {
     const uint32_t S = 1u << (K - 1), M = 1u << n;
-    return RegsShape{(S + 31) / 32, metric == VDEC_SOFT_F32 ? (size_t)(K - 1) * 3 * 32 * (iq ? 8 : M * 4) : 0};
+    const uint32_t ng = (M == 8 && !iq) ? VDEC_RING_NG_M8 : 3;          // SoftRing / IqRing: NG groups of K-1 steps
+    return RegsShape{(S + 31) / 32, metric == VDEC_SOFT_F32 ? (size_t)(K - 1) * ng * 32 * (iq ? 8 : M * 4) : 0};
 }
 
 // `kern` is a __global__ symbol of this library or a cudaKernel_t of a run-time compiled module
@@ -897,7 +915,8 @@ template <class CD, class MP>
 int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path_metric, uint32_t* surv, cudaStream_t st) {
     using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
     constexpr RegsShape sh{(uint32_t)CD::NW, Feeder::kWarpBytes};
-    static_assert(Feeder::kWarpBytes == (MP::kMetric == VDEC_SOFT_F32 ? (size_t)CD::B * 3 * 32 * (kIsIq<MP> ? 8 : CD::M * 4) : 0),
+    static_assert(Feeder::kWarpBytes == (MP::kMetric == VDEC_SOFT_F32
+                                             ? (size_t)CD::B * ((CD::M == 8 && !kIsIq<MP>) ? VDEC_RING_NG_M8 : 3) * 32 * (kIsIq<MP> ? 8 : CD::M * 4) : 0),
                   "regs_shape() must describe the feeder");
     return regs_launch_kernel(reinterpret_cast<const void*>(&vit_regs_kernel<CD, MP>), sh, g, in, out, path_metric, surv, st);
 }
