@@ -58,6 +58,9 @@
 #ifndef VDEC_RING_CA_M8
 #define VDEC_RING_CA_M8 1
 #endif
+#ifndef VDEC_RING_NG_M4
+#define VDEC_RING_NG_M4 3        // groups of the rate-1/2 ring
+#endif
 #ifndef VDEC_RING_NG_M8
 #define VDEC_RING_NG_M8 2        // groups of the rate-1/3 ring
 #endif
@@ -431,7 +434,7 @@ struct SoftRing {
     static constexpr int kPieces = kStepBytes / PB;            // pieces per step
     static constexpr int G = B;                                // steps per prefetch group = one rotation period,
                                                                // so the prefetch sits at phase 0 only (no per-step test)
-    static constexpr int NG = (M == 8) ? VDEC_RING_NG_M8 : 3;  // groups in the ring
+    static constexpr int NG = (M == 8) ? VDEC_RING_NG_M8 : VDEC_RING_NG_M4;  // groups in the ring
     static constexpr int kSlots = G * NG;
     static constexpr size_t kWarpBytes = (size_t)kSlots * 32 * kStepBytes;   // K=7, n=2: 9 KB
     static_assert(M == 4 || M == 8, "soft ring feeder supports n = 2, 3");
@@ -887,7 +890,7 @@ struct RegsShape {
 };
 inline RegsShape regs_shape(uint32_t K, uint32_t n, uint32_t metric, bool iq = false) {
     const uint32_t S = 1u << (K - 1), M = 1u << n;
-    const uint32_t ng = (M == 8 && !iq) ? VDEC_RING_NG_M8 : 3;          // SoftRing / IqRing: NG groups of K-1 steps
+    const uint32_t ng = iq ? 3 : (M == 8 ? VDEC_RING_NG_M8 : VDEC_RING_NG_M4);      // SoftRing / IqRing: NG groups of K-1 steps
     return RegsShape{(S + 31) / 32, metric == VDEC_SOFT_F32 ? (size_t)(K - 1) * ng * 32 * (iq ? 8 : M * 4) : 0};
 }
 
@@ -916,7 +919,7 @@ int regs_launch(const LaunchGeom& g, const void* in, uint8_t* out, int32_t* path
     using Feeder = typename FeederOf<MP, CD::M, CD::B>::type;
     constexpr RegsShape sh{(uint32_t)CD::NW, Feeder::kWarpBytes};
     static_assert(Feeder::kWarpBytes == (MP::kMetric == VDEC_SOFT_F32
-                                             ? (size_t)CD::B * ((CD::M == 8 && !kIsIq<MP>) ? VDEC_RING_NG_M8 : 3) * 32 * (kIsIq<MP> ? 8 : CD::M * 4) : 0),
+                                             ? (size_t)CD::B * (kIsIq<MP> ? 3 : (CD::M == 8 ? VDEC_RING_NG_M8 : VDEC_RING_NG_M4)) * 32 * (kIsIq<MP> ? 8 : CD::M * 4) : 0),
                   "regs_shape() must describe the feeder");
     return regs_launch_kernel(reinterpret_cast<const void*>(&vit_regs_kernel<CD, MP>), sh, g, in, out, path_metric, surv, st);
 }
