@@ -400,10 +400,23 @@ template <int NW> struct SurvWord;
 template <> struct SurvWord<1> { using type = uint32_t; };
 template <> struct SurvWord<2> { using type = uint2; };
 
+// survivor words are written once and read back ~0.7 ms later from L2 / HBM: VDEC_SURV_ST picks the store's cache
+// operator (0 = default write-back, 1 = .cg: L2 only, 2 = .cs: streaming) so that they do not displace the input
+// sectors that the ring's cp.async.ca keeps in L1
+#ifndef VDEC_SURV_ST
+#define VDEC_SURV_ST 1
+#endif
 template <int NW>
 __device__ __forceinline__ void surv_store(uint32_t* p, const uint32_t (&dw)[NW]) {
-    if constexpr (NW == 1) *p = dw[0];
-    else *reinterpret_cast<uint2*>(p) = make_uint2(dw[0], dw[1]);
+    if constexpr (NW == 1) {
+        if constexpr (VDEC_SURV_ST == 1) __stcg(p, dw[0]);
+        else if constexpr (VDEC_SURV_ST == 2) __stcs(p, dw[0]);
+        else *p = dw[0];
+    } else {
+        if constexpr (VDEC_SURV_ST == 1) __stcg(reinterpret_cast<uint2*>(p), make_uint2(dw[0], dw[1]));
+        else if constexpr (VDEC_SURV_ST == 2) __stcs(reinterpret_cast<uint2*>(p), make_uint2(dw[0], dw[1]));
+        else *reinterpret_cast<uint2*>(p) = make_uint2(dw[0], dw[1]);
+    }
 }
 
 // lowest-index argmin over LOGICAL states when the registers are in rotation phase PH
