@@ -77,6 +77,7 @@ template <int K_, int N_, uint64_t P0_, uint64_t P1_, uint64_t P2_, bool REF_>
 struct CodeDef {
     static constexpr int K = K_, N = N_, B = K_ - 1, S = 1 << (K_ - 1), M = 1 << N_;
     static constexpr int NW = (S + 31) / 32;
+    static constexpr bool REF = REF_;
     // resident CTAs per SM the register budget is cut for.  Measured (tools/bench_configs.py, A/B of
     // builds): labellings with fewer shared candidate sums, and n = 3, spill at 128 registers and run
     // 5 % faster with 168 registers and 3 CTAs; the reference-labelled (171,133) code prefers 4.

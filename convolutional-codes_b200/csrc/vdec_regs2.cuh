@@ -97,6 +97,16 @@ __device__ __forceinline__ void packed_bm(uint2 x, uint32_t (&bm)[M]) {
 #ifndef VDEC_REGS2_SPLIT
 #define VDEC_REGS2_SPLIT 1
 #endif
+#ifndef VDEC_R2_PF_BYTES
+#define VDEC_R2_PF_BYTES 32       // input rows: L1 prefetch distance in bytes (0 = none), see prefetch_rows
+#endif
+#ifndef VDEC_R2_MINB_LIN
+#define VDEC_R2_MINB_LIN 3        // CTAs per SM of the 64-state kernels with true-parity labels: 16 distinct label pairs spill at 128 registers
+#endif
+// 64-state kernels whose labelling uses all M * M label pairs (true-parity labels, and rate 1/3 with either labelling):
+// the table of pair constants does not fit next to 64 metric registers at 128 registers per thread
+template <class CD> constexpr bool kRegs2Wide = CD::S >= 64 && (!CD::REF || CD::N == 3);
+template <class CD> constexpr int kRegs2MinBlocks = kRegs2Wide<CD> ? VDEC_R2_MINB_LIN : 4;
 // a - b that ptxas does not merge with a following add into one 3-input IADD3
 __device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b) {
     uint32_t d;
@@ -192,7 +202,7 @@ __device__ __forceinline__ uint32_t surv_word(const typename SurvVec<NW>::type& 
 constexpr int kTrace2Chunk = 16;
 
 template <class CD, int MODE>
-__global__ void __launch_bounds__(kRegsThreads, 4)
+__global__ void __launch_bounds__(kRegsThreads, kRegs2MinBlocks<CD>)
 vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t* __restrict__ path_metric,
                  uint32_t* __restrict__ surv, uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t tile_bytes,
                  uint32_t stride_steps, uint32_t init_all_from) {
@@ -213,6 +223,21 @@ vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t
     const Elem* rowA = static_cast<const Elem*>(in) + (size_t)min(fA, nframes - 1) * stride_steps;
     const Elem* rowB = static_cast<const Elem*>(in) + (size_t)min(fB, nframes - 1) * stride_steps;
     auto fetch = [&](uint32_t t) { return make_uint2((uint32_t)__ldg(rowA + t), (uint32_t)__ldg(rowB + t)); };
+    // the loads above run one step ahead of the ACS, which covers an L1 hit but not the first touch of a 32-byte
+    // sector (every 32nd step hard, every 8th quantised): an L1 prefetch kPfSteps further on brings the sector in
+    // while the current one is consumed (no register, two LSU slots per B steps).  Measured on the 64-state kernels
+    // with true-parity labels (hard 141.4 -> 146.0, quantised 131.6 -> 139.0 Gbit/s; with 168 registers and 3 CTAs per SM,
+    // i.e. without their spills, 148.6 and 144.9; rate 1/3 with reference labels 141.8 -> 148.5); with the reference's labels the
+    // kernel sits at its instruction-mix limit either way (+-1 %), and on the 4-state codebook trellis, where a
+    // B-step group is a few dozen instructions, the two extra LSU slots cost a third (659 -> 430): kRegs2Wide only.
+    constexpr uint32_t kPfSteps = kRegs2Wide<CD> ? VDEC_R2_PF_BYTES / sizeof(Elem) : 0;
+    auto prefetch_rows = [&](uint32_t t) {
+        if constexpr (kPfSteps != 0) {
+            const uint32_t tp = min(t + kPfSteps, T - 1);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(rowA + tp));
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(rowB + tp));
+        }
+    };
     SV* sv = reinterpret_cast<SV*>(surv) + (size_t)gw * T * 32 + lane;
 
     uint32_t r[S];
@@ -233,6 +258,7 @@ vit_regs2_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, int32_t
 
     uint32_t t = 0;
     for (; t + B <= T; t += B) {
+        prefetch_rows(t);
         static_for<0, B>([&](auto phc) {
             constexpr int PH = decltype(phc)::value;
             const uint2 x = xn;

@@ -5,6 +5,7 @@ decoded Gbit/s and ACS Gstate-updates/s per kernel family, CUDA-event timed, inp
     python tools/bench_configs.py [--quick]
 """
 import argparse
+import re
 import json
 import os
 import sys
@@ -19,7 +20,7 @@ def main():
     cc = vdec_pkg.load()
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="", help="substring filter on the case name")
+    ap.add_argument("--only", default="", help="filter on the case name: substring, or regular expression")
     args = ap.parse_args()
     q = 8 if args.quick else 1
     C = cc.codes
@@ -30,10 +31,14 @@ def main():
         ("C2 soft K7 r1/2 L1024 ref", C.K7_R12, cc.SOFT_F32, cc.PARITY_REF, 1000000 // q, 0),
         ("C2 soft K7 r1/2 L1024 linear", C.K7_R12, cc.SOFT_F32, cc.PARITY_LINEAR, 1000000 // q, 0),
         ("C2h hard K7 r1/2 L1024", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, 0),
+        ("C2h hard K7 r1/2 L1024 ref-labels", C.K7_R12, cc.HARD_U16, cc.PARITY_REF, 1000000 // q, 0),
+        ("f3 quant K7 r1/2 L1024 ref-labels (u8 metrics <= 7)", C.K7_R12, cc.SOFT_U8, cc.PARITY_REF, 1000000 // q, 0),
         ("C2h hard K7 r1/2 L1024 (32-bit kernel)", C.K7_R12, cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, cc.PREFER_32BIT),
         ("f3 quant K7 r1/2 L1024 (u8 metrics <= 7)", C.K7_R12, cc.SOFT_U8, cc.PARITY_LINEAR, 1000000 // q, 0),
         ("C3 soft K7 r1/3 L1024 ref", C.K7_R13, cc.SOFT_F32, cc.PARITY_REF, 511488 // q, 0),
         ("C3 soft K7 r1/3 L1024 linear", C.K7_R13, cc.SOFT_F32, cc.PARITY_LINEAR, 511488 // q, 0),
+        ("C3h hard K7 r1/3 L1024 ref-labels", C.K7_R13, cc.HARD_U16, cc.PARITY_REF, 1000000 // q, 0),
+        ("C3h hard K7 r1/3 L1024", C.K7_R13, cc.HARD_U16, cc.PARITY_LINEAR, 1000000 // q, 0),
         # polynomials outside the registries: the same kernel families, compiled at run time by NVRTC (vdec_jit.cu)
         ("K7 (165,127) soft L1024, nvrtc", cc.CodeParam(2, 7, 1024, (C.left_align("165", 7), C.left_align("127", 7))), cc.SOFT_F32, cc.PARITY_LINEAR, 1000000 // q, 0),
         ("K7 (165,127) soft L1024, table-driven", cc.CodeParam(2, 7, 1024, (C.left_align("165", 7), C.left_align("127", 7))), cc.SOFT_F32, cc.PARITY_LINEAR, 8192 // q, cc.NO_JIT),
@@ -82,7 +87,7 @@ def main():
         dec.close(); del x
         torch.cuda.empty_cache()
     for name, code, metric, parity, F, flags in cases:
-        if args.only and args.only not in name:
+        if args.only and args.only not in name and not re.search(args.only, name):
             continue
         dec = cc.BatchDecoder(code, metric, parity, flags=flags, metric_max=7 if metric == cc.SOFT_U8 else 0)
         if metric == cc.SOFT_F32:
