@@ -49,6 +49,25 @@ VDEC_HD constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return
 #define VDEC_TILE_TM_MAX 128
 #endif
 VDEC_HD constexpr bool tile_thread_major(uint32_t tpf) { return tpf >= VDEC_TILE_TM_MIN && tpf <= VDEC_TILE_TM_MAX; }
+// Window-major, staged: [warp of the grid][window][lane][6 steps], 48 bytes per lane and window.  The lanes park the six
+// words of a window in their warp's (idle) exchange region and the warp writes the 1536-byte record with three fully
+// coalesced 16-byte stores per lane; the traceback reads a window's 48 bytes as three 16-byte loads out of two sectors
+// instead of six.  Needs a warp-private exchange region, i.e. at most 32 threads per frame (K <= 12).
+// Measured against the layouts above (profiles/r02z_ab_tile_window_major.txt): K = 8 +3.3 %, K = 9 +3.5 %, K = 10 +2.6 %,
+// K = 11 +2.2 %, K = 12 +0.7 %; K = 9 with the de-facto labels, whose windows already expand their metrics through
+// shared memory, -0.9 % — hence true-parity labels only.
+#ifndef VDEC_TILE_WM_MIN
+#define VDEC_TILE_WM_MIN 1
+#endif
+#ifndef VDEC_TILE_WM_MAX
+#define VDEC_TILE_WM_MAX 32
+#endif
+enum { kSurvStepMajor = 0, kSurvThreadMajor = 1, kSurvWindowMajor = 2 };
+VDEC_HD constexpr int tile_surv_layout(uint32_t tpf, bool ref) {
+    return (!ref && tpf <= 32 && tpf >= VDEC_TILE_WM_MIN && tpf <= VDEC_TILE_WM_MAX) ? kSurvWindowMajor
+           : tile_thread_major(tpf) ? kSurvThreadMajor : kSurvStepMajor;
+}
+constexpr uint32_t kWmRecordBytes = 32 * 6 * 8;     // one warp, one window
 
 // N_ = 3 (rate 1/3, 8 metrics per step, third polynomial P2_): true-parity labels only — the de-facto labelling would
 // need a 64-letter extended alphabet.
@@ -63,7 +82,9 @@ struct TileDef {
     static_assert(K_ >= 8 && K_ <= 15, "register-tile kernel covers K = 8 .. 15");
     static_assert(K_ > 8 || VB_ <= 1, "K = 8: the reader's second register bit is a register bit of the writer too, so at most 2 registers per LDS");
     static constexpr int FPC = kTileThreads / TPF;            // frames per CTA
-    static constexpr bool kThreadMajor = tile_thread_major(TPF);   // survivor layout, see VDEC_TILE_TM_MIN / _MAX
+    static constexpr int kLayout = tile_surv_layout(TPF, REF_);           // survivor layout, see VDEC_TILE_TM_MIN / _MAX, VDEC_TILE_WM_MIN / _MAX
+    static constexpr bool kThreadMajor = kLayout == kSurvThreadMajor;
+    static constexpr bool kWindowMajor = kLayout == kSurvWindowMajor;
     static constexpr bool kSign = K_ >= 9;                    // sign-based decisions (vdec_regs.cuh kDecSign): K = 8 loses 7 % with them
     static constexpr int RT = TPF > 32 ? TPF : 32;            // threads sharing one exchange region
     static constexpr int RTB = ilog2(RT);
@@ -286,6 +307,20 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
     if (tau == 0) rp[0] = pack2(0.f, rest);
 
     uint2* sv = TD::kThreadMajor ? surv + ((size_t)f * TPF + tau) * T : surv + (size_t)f * T * TPF + tau;
+    // window-major: this warp's records, one per window; the words of the current window wait in the exchange region
+    [[maybe_unused]] uint4* wmp = reinterpret_cast<uint4*>(surv) +
+                                  (size_t)(blockIdx.x * (kTileThreads / 32) + (tid >> 5)) * ((T + 5) / 6) * (kWmRecordBytes / 16) + lane;
+    [[maybe_unused]] uint2* stage2 = reinterpret_cast<uint2*>(xbuf) + lane * 6;
+    [[maybe_unused]] const uint4* stage4 = reinterpret_cast<const uint4*>(xbuf) + lane;
+    auto flush_window = [&]() {
+        if constexpr (TD::kWindowMajor) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 3; ++j) __stcg(wmp + j * 32, stage4[j * 32]);
+            wmp += kWmRecordBytes / 16;
+            __syncwarp();                                   // the transpose reuses the region
+        }
+    };
     uint32_t t = 0;
     auto begin_window = [&]() {
         prefetch();
@@ -309,12 +344,14 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
         if constexpr (TD::REF) tile_get_pairs<CD, KS, 2 + FSH>(vma + KS * (64 << FSH), xt[KS], bp);
         else tile_get_pairs<CD, KS>(ring + roff + KS * SB, xt[KS], bp);
         acs_step_f2<CD, KS>(rp, bp, dw);
-        if (live) sv[TD::kThreadMajor ? (size_t)(t + KS) : (size_t)(t + KS) * TPF] = make_uint2(dw[0], dw[1]);
+        if constexpr (TD::kWindowMajor) stage2[KS] = make_uint2(dw[0], dw[1]);
+        else if (live) sv[TD::kThreadMajor ? (size_t)(t + KS) : (size_t)(t + KS) * TPF] = make_uint2(dw[0], dw[1]);
     };
     // full windows that are followed by another one: straight-line 6 steps, then the transpose
     for (; t + 6 < T; t += 6) {
         begin_window();
         static_for<0, 6>(step);
+        flush_window();
         roff = (roff == (kTileRingGroups - 1) * GB) ? 0u : roff + GB;
         // ---- transpose: sigma' = rotr(sigma, 6) -------------------------------------------------------
         static_for<0, 64>([&](auto ac) {
@@ -346,6 +383,7 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
     const uint32_t n = T - t;
     begin_window();
     static_for<0, 6>([&](auto kc) { if ((int)n > (decltype(kc)::value)) step(kc); });
+    flush_window();
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
     // ---- final state: lowest LOGICAL index among the minima (:72-79); logical = rotr_B(sigma, k+1) ---------
@@ -391,14 +429,17 @@ vit_tile_forward(const float* __restrict__ in, uint2* __restrict__ surv, uint32_
 // (cur & (2^(5-k) - 1)) | (cur >> (B-1-k)) << (5-k) of thread (cur >> (5-k)) & (TPF-1)'s word; the thread index is
 // the same for every step of a window, so a window's words are fetched together.  Output as in vdec_regs.cuh:
 // the state doubles as a shift register of decoded bits, 16 of which are emitted every 16 steps (:81-89).
-// THREAD_MAJOR: survivor layout [frame][thread][step] (tile_thread_major); SIGN: rotated survivor-bit layout (TileDef::kSign)
-template <bool THREAD_MAJOR, bool SIGN>
+// LAYOUT: survivor layout (tile_surv_layout); SIGN: rotated survivor-bit layout (TileDef::kSign)
+template <int LAYOUT, bool SIGN>
 static __global__ void __launch_bounds__(128)
 vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ final_state, uint8_t* __restrict__ out,
                    uint32_t nframes, uint32_t T, uint32_t out_bytes, uint32_t B, uint32_t TPF) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;
     const uint2* sv = surv + (size_t)f * T * TPF;
+    // window-major: the frame's threads are threads (f % FPC) * TPF .. of block f / FPC of the forward grid
+    [[maybe_unused]] const uint32_t FPC = kTileThreads / TPF, nwin = (T + 5) / 6;
+    [[maybe_unused]] const uint32_t tid0 = (f % FPC) * TPF, blk = f / FPC;
     uint8_t* row = out + (size_t)f * out_bytes;
     const uint32_t S1 = (1u << B) - 1u;
     uint32_t h = final_state[f];
@@ -406,9 +447,21 @@ vit_tile_traceback(const uint2* __restrict__ surv, const uint32_t* __restrict__ 
         const int n = (int)T - w0 < 6 ? (int)T - w0 : 6;
         const uint32_t owner = ((h & S1) >> (6 - n)) & (TPF - 1);
         uint2 wd[6];
+        if constexpr (LAYOUT == kSurvWindowMajor) {
+            const uint32_t otid = tid0 + owner;
+            const uint4* rec = reinterpret_cast<const uint4*>(surv) +
+                               ((size_t)(blk * (kTileThreads / 32) + (otid >> 5)) * nwin + (uint32_t)w0 / 6) * (kWmRecordBytes / 16) + (otid & 31u) * 3;
 #pragma unroll
-        for (int k = 0; k < 6; ++k)
-            if (k < n) wd[k] = __ldcg(THREAD_MAJOR ? sv + (size_t)owner * T + (w0 + k) : sv + (size_t)(w0 + k) * TPF + owner);
+            for (int j = 0; j < 3; ++j) {
+                const uint4 q = __ldcg(rec + j);
+                wd[2 * j] = make_uint2(q.x, q.y);
+                wd[2 * j + 1] = make_uint2(q.z, q.w);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (k < n) wd[k] = __ldcg(LAYOUT == kSurvThreadMajor ? sv + (size_t)owner * T + (w0 + k) : sv + (size_t)(w0 + k) * TPF + owner);
+        }
 #pragma unroll
         for (int k = 5; k >= 0; --k) {
             if (k >= n) continue;
@@ -440,15 +493,23 @@ inline TileShape tile_shape(uint32_t K, bool ref, uint32_t n = 2) {
     const uint32_t tpf = 1u << (K - 7);
     return TileShape{K - 1, tpf, (uint32_t)kTileThreads / tpf, ref, K >= 9, n};
 }
-inline size_t tile_surv_bytes_tpf(const LaunchGeom& g, uint32_t tpf) {
-    return (size_t)g.nframes * g.T * tpf * sizeof(uint2) + (size_t)g.nframes * sizeof(uint32_t);
+// survivor words of one launch: per frame T * TPF words, or whole records of every warp of the forward grid (window-major)
+inline size_t tile_surv_only_bytes(const LaunchGeom& g, const TileShape& sh) {
+    if (tile_surv_layout(sh.TPF, sh.ref) == kSurvWindowMajor) {
+        const size_t blocks = (g.nframes + sh.FPC - 1) / sh.FPC;
+        return blocks * (kTileThreads / 32) * ((g.T + 5) / 6) * kWmRecordBytes;
+    }
+    return (size_t)g.nframes * g.T * sh.TPF * sizeof(uint2);
+}
+inline size_t tile_surv_bytes_shape(const LaunchGeom& g, const TileShape& sh) {
+    return tile_surv_only_bytes(g, sh) + (size_t)g.nframes * sizeof(uint32_t);
 }
 
 // `kern`: vit_tile_forward<TD> of this library or a cudaKernel_t of a run-time compiled module
 inline int tile_launch_kernel(const void* kern, const TileShape& sh, const LaunchGeom& g, const void* in, uint8_t* out,
                               uint32_t* scratch, cudaStream_t st) {
     uint2* surv = reinterpret_cast<uint2*>(scratch);
-    uint32_t* final_state = reinterpret_cast<uint32_t*>(surv + (size_t)g.nframes * g.T * sh.TPF);
+    uint32_t* final_state = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(scratch) + tile_surv_only_bytes(g, sh));
     const size_t smem = (size_t)kTileThreads * 64 * 4 + (((size_t)sh.FPC * tile_ring_bytes((int)sh.n) + 511) & ~(size_t)511) +
                         (sh.ref ? (size_t)sh.FPC * kTileVmBytes : 0) + (kTileThreads / 32) * 8;
     VDEC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -458,22 +519,24 @@ inline int tile_launch_kernel(const void* kern, const TileShape& sh, const Launc
     void* args[] = {&inf, &surv, &final_state, &nframes, &T, &stride, &init_all_from};
     VDEC_CUDA(cudaLaunchKernel(kern, dim3(blocks), dim3(kTileThreads), args, smem, st));
     const uint32_t tb_blocks = (g.nframes + 127) / 128;
-    const bool tm = tile_thread_major(sh.TPF);
-    if (tm && sh.sign) vit_tile_traceback<true, true><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
-    else if (tm) vit_tile_traceback<true, false><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
-    else if (sh.sign) vit_tile_traceback<false, true><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
-    else vit_tile_traceback<false, false><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF);
+    const int layout = tile_surv_layout(sh.TPF, sh.ref);
+#define VDEC_TILE_TB(L, SG) vit_tile_traceback<L, SG><<<tb_blocks, 128, 0, st>>>(surv, final_state, out, g.nframes, g.T, g.out_bytes, sh.B, sh.TPF)
+    if (layout == kSurvWindowMajor) { if (sh.sign) VDEC_TILE_TB(kSurvWindowMajor, true); else VDEC_TILE_TB(kSurvWindowMajor, false); }
+    else if (layout == kSurvThreadMajor) { if (sh.sign) VDEC_TILE_TB(kSurvThreadMajor, true); else VDEC_TILE_TB(kSurvThreadMajor, false); }
+    else { if (sh.sign) VDEC_TILE_TB(kSurvStepMajor, true); else VDEC_TILE_TB(kSurvStepMajor, false); }
+#undef VDEC_TILE_TB
     VDEC_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <class TD>
-size_t tile_surv_bytes(const LaunchGeom& g) { return tile_surv_bytes_tpf(g, TD::TPF); }
+constexpr TileShape tile_shape_of() { return TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF, TD::kSign, (uint32_t)TD::N}; }
+template <class TD>
+size_t tile_surv_bytes(const LaunchGeom& g) { return tile_surv_bytes_shape(g, tile_shape_of<TD>()); }
 
 template <class TD>
 int tile_launch(const LaunchGeom& g, const void* in, uint8_t* out, uint32_t* scratch, cudaStream_t st) {
-    return tile_launch_kernel(reinterpret_cast<const void*>(&vit_tile_forward<TD>),
-                              TileShape{(uint32_t)TD::B, (uint32_t)TD::TPF, (uint32_t)TD::FPC, TD::REF, TD::kSign, (uint32_t)TD::N}, g, in, out, scratch, st);
+    return tile_launch_kernel(reinterpret_cast<const void*>(&vit_tile_forward<TD>), tile_shape_of<TD>(), g, in, out, scratch, st);
 }
 
 struct TileEntry {
