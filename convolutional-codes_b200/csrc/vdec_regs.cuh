@@ -291,7 +291,7 @@ VDEC_HD constexpr bool pair_used(int I) {
 #ifndef VDEC_DEC_SIGN
 #define VDEC_DEC_SIGN 1
 #endif
-// Measured (gpurun_out/configs_s3n.jsonl vs configs_s3m.jsonl): K = 7 (171,133) reference labels 107.3 -> 110.0 Gbit/s
+// Measured (round-1 A/B builds; repeated in round 2, profiles/r02c_ab_operand_fetch_and_sign_decisions.txt): K = 7 (171,133) reference labels 107.3 -> 110.0 Gbit/s
 // (1503 -> 1181 instructions per 6 steps), tile kernels K = 9 +3 %, K = 15 +2 %; the linear K = 7 code (-1.6 %) and
 // rate 1/3 (-5 %) lose, so a code opts in through kSignDecisions.
 template <class CD> constexpr bool kDecSign = VDEC_DEC_SIGN && CD::B == 6 && CD::S == 64 && CD::kSignDecisions;
@@ -439,7 +439,7 @@ __device__ __forceinline__ void argmin_phase(const typename MP::T (&r)[CD::S], t
 // No cross-lane sharing, hence no barrier: cp.async.wait_group is all the synchronisation needed.
 // PB = bytes per cp.async piece.  PB = 16: one LDGSTS per 4 metrics, a lane's piece is 16 contiguous bytes, so
 // the scalar operand loads of a warp hit 8 banks (4-way conflict).  PB = 4: one LDGSTS per metric (cp.async.ca),
-// words interleaved across lanes, every operand load is conflict-free.  Measured (gpurun_out/call_r1o.log): the four
+// words interleaved across lanes, every operand load is conflict-free.  Measured (round-1 A/B build): the four
 // times more LDGSTS requests cost far more than the conflicts (n = 2: 107.5 -> 85.7 Gbit/s, n = 3: 68.0 -> 35.7),
 // so PB = 16 is the default for both; PB = 4 stays selectable for A/B builds (VDEC_RING_PB_M4 / _M8).
 template <int M, int B, int PB>

@@ -82,6 +82,13 @@ struct CommSet { std::vector<int> ids; std::vector<ncclComm_t> comm; };
 std::vector<CommSet> g_comms;
 std::mutex g_sweep_mu;                 // one sweep at a time per process: the communicators and their streams are shared
 
+// the caller's current device is put back when the sweep returns (it runs cudaSetDevice for every device it uses)
+struct DeviceRestore {
+    int dev = -1;
+    DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) dev = -1; }
+    ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
 struct Sweep {
     std::vector<Dev> dev;
     ncclComm_t* comm = nullptr;
@@ -125,6 +132,7 @@ extern "C" int vdec_sweep(const struct vdec_config* cfg, const struct vdec_sweep
     if (!bsc && cfg->metric != VDEC_SOFT_F32) { set_error("vdec_sweep: the AWGN channels need VDEC_SOFT_F32"); return -1; }
 
     std::lock_guard<std::mutex> lock(g_sweep_mu);
+    DeviceRestore restore;                                          // destroyed after `s`, whose destructor switches devices
     Sweep s;
     s.dev.resize(ndev);
     // frames per launch and device: four full waves of the register kernels (148 SMs x 4 CTAs x 128 frames)
@@ -150,8 +158,9 @@ extern "C" int vdec_sweep(const struct vdec_config* cfg, const struct vdec_sweep
         for (int r = 0; r < ndev; ++r) ids[r] = s.dev[r].id;
         for (CommSet& c : g_comms) if (c.ids == ids) s.comm = c.comm.data();
         if (!s.comm) {
-            g_comms.push_back(CommSet{ids, std::vector<ncclComm_t>(ndev, nullptr)});
-            VDEC_NCCL(g_nccl.CommInitAll(g_comms.back().comm.data(), ndev, ids.data()));
+            CommSet fresh{ids, std::vector<ncclComm_t>(ndev, nullptr)};
+            VDEC_NCCL(g_nccl.CommInitAll(fresh.comm.data(), ndev, ids.data()));     // nothing is cached when this fails
+            g_comms.push_back(std::move(fresh));
             s.comm = g_comms.back().comm.data();
         }
     }

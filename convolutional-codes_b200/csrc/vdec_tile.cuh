@@ -39,7 +39,7 @@ VDEC_HD constexpr int ilog2(int v) { int r = 0; while ((1 << r) < v) ++r; return
 // Survivor layout.  Step-major [frame][step][thread] lets the frame's threads store one contiguous record per step, but
 // the traceback needs ONE thread's word per step and fetches a 32-byte sector for it.  Thread-major
 // [frame][thread][step] makes a window's words 48 contiguous bytes for the traceback; the forward stores become 8-byte
-// pieces that L2 merges into sectors.  Measured on the same box (gpurun_out/ab_s3x.log, ab_s3y.log, ab_s3zy.log, ab_s3k1.log),
+// pieces that L2 merges into sectors.  Measured on the same box (round-1 A/B builds),
 // thread-major against step-major: K = 8 -5 %, K = 9 +-0, K = 10 +2.5 %, K = 11 +5.8 %, K = 12 +1.2 %, K = 13 +1 %, K = 14 +1.7 %, K = 15 -1.5 %; hence thread-major
 // for 8 .. 128 threads per frame (K = 10 .. 14).
 #ifndef VDEC_TILE_TM_MIN

@@ -25,6 +25,10 @@
  * All functions return 0 on success and -1 on failure, as the reference API does;
  * vdec_last_error() gives the reason.  There is no CPU fallback: without a CUDA
  * device every compute entry point fails.
+ *
+ * CUDA device: a handle belongs to vdec_config.device; every entry point that takes
+ * a handle makes that device current (cudaSetDevice) and leaves it current.
+ * vdec_sweep, which drives several devices, puts the caller's device back.
  */
 #ifndef VDEC_H
 #define VDEC_H
@@ -208,7 +212,7 @@ enum vdec_channel {
 struct vdec_sweep_config {
     uint64_t seed;
     uint64_t frames_per_batch;    /* frames per point and batch, all devices together */
-    uint64_t max_frames;          /* with min_frame_errors: give up on a point after this many frames (0 = no limit) */
+    uint64_t max_frames;          /* with min_frame_errors: give up on a point after this many frames (0 = no limit: an error-free point never ends) */
     uint64_t min_frame_errors;    /* 0 = one batch per point */
     uint32_t chunk_frames;        /* frames per launch and device, 0 = 303104 (four full waves of the register kernels) */
     uint32_t channel;             /* enum vdec_channel */
