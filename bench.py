@@ -331,11 +331,12 @@ def run_gpu(args) -> int:
     for w in works:
         w.wait()
     works.clear()
-    barrier()
     l0 = dec.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
+    clk = ClockSampler(local)                             # NVML start-up (tens of ms, different on every rank) stays outside
+    with clk:
+        barrier()                                         # the ranks enter the timed region together: a late rank would be
+        e0.record()                                       # waited for in the first all-reduce and billed to all the others
         for i in range(args.steps):
             step(max(args.warmup, 0) + i, timed=True)
         for w in works:                                   # every step's collective has completed before the clock stops
