@@ -42,7 +42,19 @@ static const char* arg(int argc, char** argv, const char* key, const char* dflt)
     return dflt;
 }
 
+static int usage(const char* prog) {
+    fprintf(stderr,
+            "usage: %s [--code cb0|cb1|cb2|cb3|cb5|k7r12|k7r13|k9|k15] [--labels ref|linear] [--channel awgn|awgn-hard|bsc]\n"
+            "          [--ebn0 first:last:step] [--frames N per batch] [--min-frame-errors N] [--max-frames N] [--block-len L]\n"
+            "          [--gpus N (0 = all)] [--seed S] [--chunk frames per launch] [--resume file] [--out file.m]\n"
+            "Eb/N0 (or, with --channel bsc, the BSC driver's 17 crossover rates) sweep on the GPUs of this node; prints one line per\n"
+            "operating point and appends result vectors in the style of the reference's results/*.m to --out.\n", prog);
+    return 2;
+}
+
 int main(int argc, char** argv) {
+    for (int i = 1; i < argc; ++i)
+        if (strcmp(argv[i], "--help") == 0 || strcmp(argv[i], "-h") == 0) return usage(argv[0]);
     const char* cname = arg(argc, argv, "--code", "k7r12");
     const char* chan = arg(argc, argv, "--channel", "awgn");            /* awgn | awgn-hard | bsc */
     const char* labels = arg(argc, argv, "--labels", "ref");            /* ref = the reference's de-facto labels | linear */
