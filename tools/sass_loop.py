@@ -29,5 +29,7 @@ for f in funcs:
         if lo <= a <= hi:
             hist[("@p " if pred.strip() and "PT" not in pred else "") + op] += 1
     n = sum(hist.values())
-    print(f"{name[:90]}\n  loop {lo:#x}..{hi:#x}: {n} instructions")
+    dem = subprocess.run(["c++filt", name.strip()], capture_output=True, text=True).stdout.strip() or name
+    dem = re.sub(r"\(unsigned long\)|\(int\)|\(bool\)|vd::", "", dem.split("(const")[0].split("(void const")[0])
+    print(f"{dem[:200]}\n  loop {lo:#x}..{hi:#x}: {n} instructions")
     print("  " + ", ".join(f"{k} {v}" for k, v in hist.most_common(40)))
